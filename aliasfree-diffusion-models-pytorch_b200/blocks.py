@@ -1,0 +1,212 @@
+"""Drop-in ``nn.Module`` blocks of the alias-free UNet (Configs B-D).
+
+Same class names, constructor arguments, forward signatures and ``state_dict`` keys as the
+reference blocks in modules/ddpm_utils.py (DoubleConv_F :97-143, Down_F :253, Up_F :276,
+Down_FF :301, Up_FF :330, Down_FFF :360, Up_FFF :389, plus the baseline DoubleConv :76,
+Down :199, Up :222, SelfAttention :54 that variants 0/1 need), so reference checkpoints
+load with ``strict=True``.  The filter taps are plain attributes (``jinc_filter``,
+``sinc_filter``), not buffers -- exactly like the reference, they are absent from the
+state_dict.
+
+What differs is the execution: every ``up -> GELU -> down`` triple is ONE launch of the
+fused CUDA kernel (ops.filtered_gelu), the residual add of the second activation is folded
+into that launch, and the standalone resamplers are single kernels as well; the 3x3
+convolutions, GroupNorm and attention stay on cuDNN / cuBLAS.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .filters import taps_from_settings
+
+
+def _conv3(cin, cout):
+    return nn.Conv2d(cin, cout, kernel_size=3, padding=1, bias=False)
+
+
+class SelfAttention(nn.Module):
+    """modules/ddpm_utils.py:54-74 (unchanged maths; stays on cuBLAS)."""
+
+    def __init__(self, channels, size):
+        super().__init__()
+        self.channels, self.size = channels, size
+        self.mha = nn.MultiheadAttention(channels, 4, batch_first=True)
+        self.ln = nn.LayerNorm([channels])
+        self.ff_self = nn.Sequential(nn.LayerNorm([channels]), nn.Linear(channels, channels),
+                                     nn.GELU(), nn.Linear(channels, channels))
+
+    def forward(self, x):
+        tokens = x.flatten(2).transpose(1, 2)                    # [B, HW, C]
+        q = self.ln(tokens)
+        att = self.mha(q, q, q, need_weights=False)[0] + tokens   # same values, no [B,L,L] weights tensor
+        att = self.ff_self(att) + att
+        return att.transpose(1, 2).reshape(-1, self.channels, self.size, self.size)
+
+
+class DoubleConv(nn.Module):
+    """Baseline (unfiltered) block, modules/ddpm_utils.py:76-95."""
+
+    def __init__(self, in_channels, out_channels, mid_channels=None, residual=False):
+        super().__init__()
+        mid = mid_channels or out_channels
+        self.residual = residual
+        self.double_conv = nn.Sequential(_conv3(in_channels, mid), nn.GroupNorm(1, mid), nn.GELU(),
+                                         _conv3(mid, out_channels), nn.GroupNorm(1, out_channels))
+
+    def forward(self, x):
+        y = self.double_conv(x)
+        return F.gelu(x + y) if self.residual else y
+
+
+class DoubleConv_F(nn.Module):
+    """conv3x3 -> GroupNorm -> [up2x -> GELU -> low-pass -> down2x] -> conv3x3 -> GroupNorm,
+    and for ``residual=True`` a second filtered GELU applied to (x + that)."""
+
+    def __init__(self, in_channels, out_channels, mid_channels=None, residual=False, f_settings=None):
+        super().__init__()
+        self.residual = residual
+        self.f_settings = f_settings
+        self.jinc_filter = taps_from_settings(f_settings, "down")
+        self.sinc_filter = taps_from_settings(f_settings, "up")
+        mid = mid_channels or out_channels
+        self.conv1 = _conv3(in_channels, mid)
+        self.norm1 = nn.GroupNorm(1, mid)
+        self.gelu = nn.GELU()          # parameter-free; kept so the module tree matches the reference
+        self.conv2 = _conv3(mid, out_channels)
+        self.norm2 = nn.GroupNorm(1, out_channels)
+        self._taps = None
+
+    def _filters(self):
+        key = (id(self.sinc_filter), id(self.jinc_filter))
+        if self._taps is None or self._taps[0] != key:      # rebuilt if a user swaps the filters
+            self._taps = (key, ops.Taps(self.sinc_filter), ops.Taps(self.jinc_filter))
+        return self._taps[1], self._taps[2]
+
+    def forward(self, x):
+        up, dn = self._filters()
+        h = self.norm1(self.conv1(x))
+        h = ops.filtered_gelu(h, up, dn)
+        h = self.norm2(self.conv2(h))
+        if self.residual:
+            h = ops.filtered_gelu(h, up, dn, residual=x)     # gelu-filter(x + h), add fused
+        return h
+
+
+class _TimeConditioned(nn.Module):
+    """Shared tail of every Down*/Up* stage: ``x + Linear(SiLU(t))`` broadcast over H, W."""
+
+    def _make_emb(self, emb_dim, out_channels):
+        self.emb_layer = nn.Sequential(nn.SiLU(), nn.Linear(emb_dim, out_channels))
+
+    def _add_emb(self, x, t):
+        return x + self.emb_layer(t)[:, :, None, None]
+
+
+def _pair(block, cin, cout, mid=None, **kw):
+    return nn.Sequential(block(cin, cin, residual=True, **kw), block(cin, cout, mid, **kw))
+
+
+class Down(_TimeConditioned):
+    """modules/ddpm_utils.py:199-220 (MaxPool, baseline blocks)."""
+
+    def __init__(self, in_channels, out_channels, emb_dim=256):
+        super().__init__()
+        blocks = _pair(DoubleConv, in_channels, out_channels)
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), blocks[0], blocks[1])
+        self._make_emb(emb_dim, out_channels)
+
+    def forward(self, x, t):
+        return self._add_emb(self.maxpool_conv(x), t)
+
+
+class Up(_TimeConditioned):
+    """modules/ddpm_utils.py:222-245 (bilinear upsample, baseline blocks)."""
+
+    def __init__(self, in_channels, out_channels, emb_dim=256):
+        super().__init__()
+        self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+        self.conv = _pair(DoubleConv, in_channels, out_channels, in_channels // 2)
+        self._make_emb(emb_dim, out_channels)
+
+    def forward(self, x, skip_x, t):
+        return self._add_emb(self.conv(torch.cat([skip_x, self.up(x)], dim=1)), t)
+
+
+class Down_F(_TimeConditioned):
+    """Config C down stage: MaxPool kept, filtered activations inside (ddpm_utils.py:253-274)."""
+
+    def __init__(self, in_channels, out_channels, emb_dim=256, f_settings=None):
+        super().__init__()
+        self.f_settings = f_settings
+        blocks = _pair(DoubleConv_F, in_channels, out_channels, f_settings=f_settings)
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), blocks[0], blocks[1])
+        self._make_emb(emb_dim, out_channels)
+
+    def forward(self, x, t):
+        return self._add_emb(self.maxpool_conv(x), t)
+
+
+class Up_F(_TimeConditioned):
+    """Config C up stage (ddpm_utils.py:276-299)."""
+
+    def __init__(self, in_channels, out_channels, emb_dim=256, f_settings=None):
+        super().__init__()
+        self.f_settings = f_settings
+        self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+        self.conv = _pair(DoubleConv_F, in_channels, out_channels, in_channels // 2, f_settings=f_settings)
+        self._make_emb(emb_dim, out_channels)
+
+    def forward(self, x, skip_x, t):
+        return self._add_emb(self.conv(torch.cat([skip_x, self.up(x)], dim=1)), t)
+
+
+class _FilteredDown(_TimeConditioned):
+    _block = None
+
+    def __init__(self, in_channels, out_channels, emb_dim=256, f_settings=None):
+        super().__init__()
+        self.f_settings = f_settings
+        self.jinc_filter = taps_from_settings(f_settings, "down")
+        kw = {"f_settings": f_settings} if self._block is DoubleConv_F else {}
+        self.conv = _pair(self._block, in_channels, out_channels, **kw)
+        self._make_emb(emb_dim, out_channels)
+
+    def forward(self, x, t):
+        return self._add_emb(self.conv(ops.custom_downsample(x, self.jinc_filter)), t)
+
+
+class _FilteredUp(_TimeConditioned):
+    _block = None
+
+    def __init__(self, in_channels, out_channels, emb_dim=256, f_settings=None):
+        super().__init__()
+        self.f_settings = f_settings
+        self.sinc_filter = taps_from_settings(f_settings, "up")
+        kw = {"f_settings": f_settings} if self._block is DoubleConv_F else {}
+        self.conv = _pair(self._block, in_channels, out_channels, in_channels // 2, **kw)
+        self._make_emb(emb_dim, out_channels)
+
+    def forward(self, x, skip_x, t):
+        up = ops.up2x(x, self.sinc_filter, out_dtype=skip_x.dtype)
+        return self._add_emb(self.conv(torch.cat([skip_x, up], dim=1)), t)
+
+
+class Down_FF(_FilteredDown):
+    """Config B: low-pass + decimate instead of MaxPool, baseline blocks (ddpm_utils.py:301-328)."""
+    _block = DoubleConv
+
+
+class Up_FF(_FilteredUp):
+    """Config B: zero-stuff + low-pass instead of bilinear (ddpm_utils.py:330-358)."""
+    _block = DoubleConv
+
+
+class Down_FFF(_FilteredDown):
+    """Config D: filtered resampling and filtered activations (ddpm_utils.py:360-387)."""
+    _block = DoubleConv_F
+
+
+class Up_FFF(_FilteredUp):
+    """Config D (ddpm_utils.py:389-417)."""
+    _block = DoubleConv_F

@@ -1,0 +1,299 @@
+// extern "C" surface of libafr_b200.so (declared in include/afr.h): argument checking,
+// taps arrangement for forward/adjoint stencils, and kernel selection.
+//
+// Stencil table (pl = (N-1)/2 and ph = N-1-pl are F.conv2d's 'same' padding split):
+//   up2x   fwd  up-like  (x,  k,        pad = pl)   -> [2H, 2W]
+//   up2x   bwd  down-like(du, flip(k),  pad = ph)   -> [H, W]
+//   down2x fwd  down-like(v,  k,        pad = pl)   -> [ceil(H/2), ceil(W/2)]
+//   down2x bwd  up-like  (dy, flip(k),  pad = ph)   -> [H, W]
+//   fused  fwd  u = up-like(x, k_up, pl_u);  y  = down-like(gelu(u),       k_dn,       pl_d)
+//   fused  bwd  dg = up-like(dy, flip(k_dn), ph_d);
+//               dx = down-like(gelu'(u) * dg, flip(k_up), ph_u)
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "afr_common.cuh"
+#include "afr_kernels.h"
+
+using namespace afr;
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local const char *g_last_kernel = "";
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_path{-1};
+
+int current_path()
+{
+    int p = g_path.load();
+    if (p < 0) {
+        const char *e = getenv("AFR_PATH");
+        p = AFR_PATH_AUTO;
+        if (e) {
+            if (!strcmp(e, "direct")) p = AFR_PATH_DIRECT;
+            else if (!strcmp(e, "tma")) p = AFR_PATH_TMA;
+            else if (!strcmp(e, "generic")) p = AFR_PATH_GENERIC;
+        }
+        g_path.store(p);
+    }
+    return p;
+}
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_status(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return AFR_OK;
+    }
+    return fail(AFR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+bool dtype_ok(int d) { return d == AFR_F32 || d == AFR_BF16; }
+size_t esz(int d) { return d == AFR_F32 ? 4 : 2; }
+bool elem_aligned(const void *p, int d) { return (reinterpret_cast<uintptr_t>(p) % esz(d)) == 0; }
+
+int check_common(int B, int C, int H, int W, const float *taps, int N)
+{
+    if (B < 0 || C < 0 || H < 1 || W < 1) return fail(AFR_ERR_BAD_SHAPE, "bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+    if ((long)H * W > (1L << 30)) return fail(AFR_ERR_BAD_SHAPE, "plane too large");
+    if (!taps) return fail(AFR_ERR_BAD_TAPS, "taps is NULL");
+    if (N < 1 || N > AFR_MAX_TAPS) return fail(AFR_ERR_BAD_TAPS, "N=%d outside [1,%d]", N, AFR_MAX_TAPS);
+    return AFR_OK;
+}
+
+void set_taps(TapsG &t, const float *k, int N, bool flip)
+{
+    t.n = N;
+    const int pl = (N - 1) / 2;
+    t.pad = flip ? (N - 1 - pl) : pl;
+    for (int i = 0; i < N * N; ++i) t.k[i] = flip ? k[N * N - 1 - i] : k[i];
+    for (int i = N * N; i < AFR_MAX_TAPS * AFR_MAX_TAPS; ++i) t.k[i] = 0.f;
+}
+
+void set_taps3(Taps3 &t, const float *k, bool flip)
+{
+    for (int i = 0; i < 9; ++i) t.k[i / 3][i % 3] = flip ? k[8 - i] : k[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+int afr_version(void) { return AFR_VERSION; }
+const char *afr_last_error(void) { return g_err; }
+const char *afr_last_kernel(void) { return g_last_kernel; }
+uint64_t afr_launch_count(void) { return g_launches.load(); }
+
+const char *afr_status_string(int s)
+{
+    switch (s) {
+    case AFR_OK: return "ok";
+    case AFR_ERR_BAD_SHAPE: return "bad shape";
+    case AFR_ERR_BAD_TAPS: return "bad taps";
+    case AFR_ERR_BAD_DTYPE: return "bad dtype";
+    case AFR_ERR_NULL_POINTER: return "null pointer";
+    case AFR_ERR_MISALIGNED: return "misaligned pointer";
+    case AFR_ERR_CUDA: return "CUDA error";
+    case AFR_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+    }
+}
+
+int afr_set_path(int path)
+{
+    int old = current_path();
+    if (path >= AFR_PATH_AUTO && path <= AFR_PATH_GENERIC) g_path.store(path);
+    return old;
+}
+
+int afr_up2x_fwd(const void *x, void *u, int B, int C, int H, int W, const float *taps, int N,
+                 int in_dtype, int out_dtype, void *stream)
+{
+    if (int rc = check_common(B, C, H, W, taps, N)) return rc;
+    if (!dtype_ok(in_dtype) || !dtype_ok(out_dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    const long planes = (long)B * C;
+    if (planes == 0) return AFR_OK;
+    if (!x || !u) return fail(AFR_ERR_NULL_POINTER, "x or u is NULL");
+    if (!elem_aligned(x, in_dtype) || !elem_aligned(u, out_dtype)) return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int path = current_path();
+    if (N == 3 && path != AFR_PATH_GENERIC && n3_up_supported(H, W, x, u, in_dtype, out_dtype)) {
+        Taps3 k; set_taps3(k, taps, false);
+        g_last_kernel = "up3_kernel";
+        return cuda_status(n3_up_like(x, u, planes, H, W, k, in_dtype, out_dtype, s), "up3_kernel");
+    }
+    TapsG t; set_taps(t, taps, N, false);
+    g_last_kernel = "up_like_generic_kernel";
+    return cuda_status(generic_up_like(x, u, planes, H, W, 2 * H, 2 * W, t, in_dtype, out_dtype, s),
+                       "up_like_generic_kernel");
+}
+
+int afr_up2x_bwd(const void *du, void *dx, int B, int C, int H, int W, const float *taps, int N,
+                 int du_dtype, int dx_dtype, void *stream)
+{
+    if (int rc = check_common(B, C, H, W, taps, N)) return rc;
+    if (!dtype_ok(du_dtype) || !dtype_ok(dx_dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    const long planes = (long)B * C;
+    if (planes == 0) return AFR_OK;
+    if (!du || !dx) return fail(AFR_ERR_NULL_POINTER, "du or dx is NULL");
+    if (!elem_aligned(du, du_dtype) || !elem_aligned(dx, dx_dtype)) return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int path = current_path();
+    if (du_dtype != dx_dtype)
+        return fail(AFR_ERR_UNSUPPORTED, "up2x_bwd needs du and dx of one dtype (cast du on the host side)");
+    if (N == 3 && path != AFR_PATH_GENERIC && n3_down_supported(2 * H, 2 * W, du, dx, du_dtype)) {
+        Taps3 k; set_taps3(k, taps, true);
+        g_last_kernel = "down3_kernel";
+        return cuda_status(n3_down_like(du, dx, planes, 2 * H, 2 * W, k, du_dtype, s), "down3_kernel");
+    }
+    TapsG t; set_taps(t, taps, N, true);
+    g_last_kernel = "down_like_generic_kernel";
+    return cuda_status(generic_down_like(du, dx, planes, 2 * H, 2 * W, H, W, t, du_dtype, s),
+                       "down_like_generic_kernel");
+}
+
+int afr_down2x_fwd(const void *v, void *y, int B, int C, int H, int W, const float *taps, int N,
+                   int dtype, void *stream)
+{
+    if (int rc = check_common(B, C, H, W, taps, N)) return rc;
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    const long planes = (long)B * C;
+    if (planes == 0) return AFR_OK;
+    if (!v || !y) return fail(AFR_ERR_NULL_POINTER, "v or y is NULL");
+    if (!elem_aligned(v, dtype) || !elem_aligned(y, dtype)) return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int path = current_path();
+    if (N == 3 && path != AFR_PATH_GENERIC && n3_down_supported(H, W, v, y, dtype)) {
+        Taps3 k; set_taps3(k, taps, false);
+        g_last_kernel = "down3_kernel";
+        return cuda_status(n3_down_like(v, y, planes, H, W, k, dtype, s), "down3_kernel");
+    }
+    TapsG t; set_taps(t, taps, N, false);
+    g_last_kernel = "down_like_generic_kernel";
+    return cuda_status(generic_down_like(v, y, planes, H, W, (H + 1) / 2, (W + 1) / 2, t, dtype, s),
+                       "down_like_generic_kernel");
+}
+
+int afr_down2x_bwd(const void *dy, void *dv, int B, int C, int H, int W, const float *taps, int N,
+                   int dtype, void *stream)
+{
+    if (int rc = check_common(B, C, H, W, taps, N)) return rc;
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    const long planes = (long)B * C;
+    if (planes == 0) return AFR_OK;
+    if (!dy || !dv) return fail(AFR_ERR_NULL_POINTER, "dy or dv is NULL");
+    if (!elem_aligned(dy, dtype) || !elem_aligned(dv, dtype)) return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int path = current_path();
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    if (N == 3 && path != AFR_PATH_GENERIC && (H % 2) == 0 && (W % 2) == 0 &&
+        n3_up_supported(Ho, Wo, dy, dv, dtype, dtype)) {
+        Taps3 k; set_taps3(k, taps, true);
+        g_last_kernel = "up3_kernel";
+        return cuda_status(n3_up_like(dy, dv, planes, Ho, Wo, k, dtype, dtype, s), "up3_kernel");
+    }
+    TapsG t; set_taps(t, taps, N, true);
+    g_last_kernel = "up_like_generic_kernel";
+    return cuda_status(generic_up_like(dy, dv, planes, Ho, Wo, H, W, t, dtype, dtype, s),
+                       "up_like_generic_kernel");
+}
+
+static int fused_common(const void *x, const void *residual, const void *dy, void *out, int B, int C,
+                        int H, int W, const float *taps_up, int N_up, const float *taps_down,
+                        int N_down, int dtype, void *stream, bool bwd)
+{
+    if (int rc = check_common(B, C, H, W, taps_up, N_up)) return rc;
+    if (int rc = check_common(B, C, H, W, taps_down, N_down)) return rc;
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    const long planes = (long)B * C;
+    if (planes == 0) return AFR_OK;
+    if (!x || !out || (bwd && !dy)) return fail(AFR_ERR_NULL_POINTER, "NULL tensor pointer");
+    if (!elem_aligned(x, dtype) || !elem_aligned(out, dtype) || (residual && !elem_aligned(residual, dtype)) ||
+        (bwd && !elem_aligned(dy, dtype)))
+        return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int path = current_path();
+    const void *ptrs[4] = {x, residual, bwd ? dy : nullptr, out};
+    if (N_up == 3 && N_down == 3 && path != AFR_PATH_GENERIC && n3_fgelu_supported(H, W, ptrs, 4, dtype)) {
+        const bool tma_ok = n3_fgelu_tma_supported(H, W, ptrs, 4, dtype);
+        if (path == AFR_PATH_TMA && !tma_ok)
+            return fail(AFR_ERR_UNSUPPORTED, "TMA path forced but shape/alignment not eligible (H=%d W=%d)", H, W);
+        const bool use_tma = (path == AFR_PATH_TMA) || (path == AFR_PATH_AUTO && tma_ok);
+        Taps3 kU, kG, kB;
+        set_taps3(kU, taps_up, false);
+        set_taps3(kG, taps_down, true);
+        set_taps3(kB, bwd ? taps_up : taps_down, bwd);
+        return cuda_status(n3_fgelu(x, residual, dy, out, planes, H, W, kU, kG, kB, bwd, dtype, use_tma, s,
+                                    &g_last_kernel),
+                           "fgelu3 kernel");
+    }
+    if (path == AFR_PATH_TMA || path == AFR_PATH_DIRECT)
+        return fail(AFR_ERR_UNSUPPORTED, "N==3 path forced but N_up=%d N_down=%d H=%d W=%d not eligible", N_up, N_down, H, W);
+    TapsG tU, tG, tB;
+    set_taps(tU, taps_up, N_up, false);
+    set_taps(tG, taps_down, N_down, true);
+    if (bwd) set_taps(tB, taps_up, N_up, true); else set_taps(tB, taps_down, N_down, false);
+    g_last_kernel = "fgelu_generic_kernel";
+    return cuda_status(generic_fgelu(x, residual, dy, out, planes, H, W, tU, tG, tB, bwd, dtype, s),
+                       "fgelu_generic_kernel");
+}
+
+int afr_filtered_gelu_fwd(const void *x, const void *residual, void *y, int B, int C, int H, int W,
+                          const float *taps_up, int N_up, const float *taps_down, int N_down,
+                          int dtype, void *stream)
+{
+    return fused_common(x, residual, nullptr, y, B, C, H, W, taps_up, N_up, taps_down, N_down, dtype,
+                        stream, false);
+}
+
+int afr_filtered_gelu_bwd(const void *x, const void *residual, const void *dy, void *dx, int B, int C,
+                          int H, int W, const float *taps_up, int N_up, const float *taps_down,
+                          int N_down, int dtype, void *stream)
+{
+    return fused_common(x, residual, dy, dx, B, C, H, W, taps_up, N_up, taps_down, N_down, dtype,
+                        stream, true);
+}
+
+int afr_rotate_periodic_cubic(const void *x, void *y, int B, int C, int H, int W, double degrees,
+                              int dtype, void *stream)
+{
+    if (B < 0 || C < 0 || H < 1 || W < 1) return fail(AFR_ERR_BAD_SHAPE, "bad shape");
+    if (dtype != AFR_F32) return fail(AFR_ERR_BAD_DTYPE, "rotate supports fp32 only");
+    if ((long)H * (W | 1) > 16384 + 128) return fail(AFR_ERR_UNSUPPORTED, "plane larger than 16384 px");
+    const long planes = (long)B * C;
+    if (planes == 0) return AFR_OK;
+    if (!x || !y) return fail(AFR_ERR_NULL_POINTER, "x or y is NULL");
+    if (x == y) return fail(AFR_ERR_UNSUPPORTED, "in-place rotate is not supported");
+    if (!elem_aligned(x, dtype) || !elem_aligned(y, dtype)) return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
+    g_last_kernel = "rotate_kernel";
+    return cuda_status(rotate_periodic_cubic((const float *)x, (float *)y, planes, H, W, degrees,
+                                             (cudaStream_t)stream),
+                       "rotate_kernel");
+}
+
+int afr_ddpm_update(void *x, const void *eps, const void *noise, int64_t n, float ca, float cb,
+                    float cc, void *stream)
+{
+    if (n < 0) return fail(AFR_ERR_BAD_SHAPE, "n < 0");
+    if (n == 0) return AFR_OK;
+    if (!x || !eps) return fail(AFR_ERR_NULL_POINTER, "x or eps is NULL");
+    g_last_kernel = "ddpm_update_kernel";
+    return cuda_status(ddpm_update((float *)x, (const float *)eps, (const float *)noise, (long)n, ca, cb,
+                                   cc, (cudaStream_t)stream),
+                       "ddpm_update_kernel");
+}
+
+}  // extern "C"

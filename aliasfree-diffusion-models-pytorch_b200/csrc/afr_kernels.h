@@ -1,0 +1,40 @@
+// Host-side launchers shared between the translation units of libafr_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "afr_common.cuh"
+
+namespace afr {
+
+// afr_generic.cu -- runtime-N kernels
+cudaError_t generic_up_like(const void *in, void *out, long planes, int Hin, int Win, int Hout,
+                            int Wout, const TapsG &t, int in_dtype, int out_dtype, cudaStream_t s);
+cudaError_t generic_down_like(const void *in, void *out, long planes, int Hin, int Win, int Hout,
+                              int Wout, const TapsG &t, int dtype, cudaStream_t s);
+cudaError_t generic_fgelu(const void *x, const void *res, const void *dy, void *out, long planes,
+                          int H, int W, const TapsG &tU, const TapsG &tG, const TapsG &tB,
+                          bool bwd, int dtype, cudaStream_t s);
+
+// afr_n3.cu -- N == 3 register-strip kernels (direct and TMA-staged)
+// All take stage taps already arranged for the stencil they run (see afr_api.cu).
+bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype);
+bool n3_fgelu_tma_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype);
+cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, void *out, long planes,
+                     int H, int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd,
+                     int dtype, bool use_tma, cudaStream_t s, const char **kernel_name);
+// up-like with N==3: in [planes,H,W] -> out [planes,2H,2W]
+bool n3_up_supported(int H, int W, const void *in, const void *out, int in_dtype, int out_dtype);
+cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,
+                       int in_dtype, int out_dtype, cudaStream_t s);
+// down-like with N==3: in [planes,H,W] (H, W even, W % 8 == 0) -> out [planes,H/2,W/2]
+bool n3_down_supported(int H, int W, const void *in, const void *out, int dtype);
+cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,
+                         int dtype, cudaStream_t s);
+
+// afr_rotate.cu
+cudaError_t rotate_periodic_cubic(const float *x, float *y, long planes, int H, int W,
+                                  double degrees, cudaStream_t s);
+cudaError_t ddpm_update(float *x, const float *eps, const float *noise, long n, float ca,
+                        float cb, float cc, cudaStream_t s);
+
+}  // namespace afr

@@ -1,0 +1,637 @@
+// N == 3 kernels (the canonical filter of the reference: kernel_size=3, Train.ipynb:101-104).
+//
+// Register-strip formulation.  A thread owns 4 adjacent output columns j..j+3 of one plane
+// and walks down R rows.  Everything that lives on the 2x grid (u, gelu(u), and for the
+// adjoint dg and gelu'(u)*dg) exists only in registers:
+//
+//   per output row i the thread needs "mid" rows 2i-1, 2i, 2i+1 at columns 2j-1 .. 2j+7;
+//   row 2i+1 of this iteration is row 2(i+1)-1 of the next, so it is carried and only two
+//   new mid rows (18 GELUs for 4 outputs) are evaluated per step -- 4.5 per output against
+//   the ideal 4.  x rows are carried the same way (one new row of 6 values per step).
+//
+// Forward:  mid = gelu(up(x; kU)),                      out = down(mid; kB), kB = k_down
+// Adjoint:  mid = gelu'(up(x; kU)) * up(dy; kG),        out = down(mid; kB),
+//           kG = flip(k_down), kB = flip(k_up)          (pads are 1/1 for N == 3)
+// mid is forced to zero outside [0,2H) x [0,2W): only column 2j-1 at j == 0 and row
+// 2i-1 at i == 0 can fall outside, which is what `first_col` / the i0 == 0 start handle.
+//
+// Two data paths feed the same core:
+//   direct  rows are read from global memory (128-bit loads + two scalars, L1-cached),
+//           used for tiny planes (4x4, 8x8) and shapes TMA cannot describe;
+//   tma     one elected thread issues cp.async.bulk.tensor (3-D box [Tw+8, Th+2, P planes],
+//           out-of-bounds zero fill = the conv's zero padding) into shared memory and the
+//           CTA waits on an mbarrier; rows then come from the staged tile.
+#include <cuda.h>
+
+#include "afr_common.cuh"
+#include "afr_kernels.h"
+
+namespace afr {
+
+// ---------------------------------------------------------------------------------
+// mid-row arithmetic
+// ---------------------------------------------------------------------------------
+// 9 columns m = 0..8  <->  X = 2j-1+m.  xa/xb hold input columns j-1 .. j+4.
+__device__ __forceinline__ void up_even_row(const float (&xa)[6], const Taps3 &k, float (&u)[9])
+{
+#pragma unroll
+    for (int m = 0; m < 9; ++m) {
+        if (m & 1) u[m] = k.k[1][1] * xa[(m + 1) / 2];
+        else u[m] = fmaf(k.k[1][2], xa[m / 2 + 1], k.k[1][0] * xa[m / 2]);
+    }
+}
+
+__device__ __forceinline__ void up_odd_row(const float (&xa)[6], const float (&xb)[6],
+                                           const Taps3 &k, float (&u)[9])
+{
+#pragma unroll
+    for (int m = 0; m < 9; ++m) {
+        if (m & 1) {
+            u[m] = fmaf(k.k[2][1], xb[(m + 1) / 2], k.k[0][1] * xa[(m + 1) / 2]);
+        } else {
+            float t = k.k[0][0] * xa[m / 2];
+            t = fmaf(k.k[0][2], xa[m / 2 + 1], t);
+            t = fmaf(k.k[2][0], xb[m / 2], t);
+            u[m] = fmaf(k.k[2][2], xb[m / 2 + 1], t);
+        }
+    }
+}
+
+template <bool kBwd>
+__device__ __forceinline__ void mid_even(const float (&xa)[6], const float (&da)[6],
+                                         const Taps3 &kU, const Taps3 &kG, bool first_col,
+                                         float (&m)[9])
+{
+    float u[9];
+    up_even_row(xa, kU, u);
+    if (kBwd) {
+        float g[9];
+        up_even_row(da, kG, g);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) m[c] = gelu_erf_grad(u[c]) * g[c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) m[c] = gelu_erf(u[c]);
+    }
+    if (first_col) m[0] = 0.f;
+}
+
+template <bool kBwd>
+__device__ __forceinline__ void mid_odd(const float (&xa)[6], const float (&xb)[6],
+                                        const float (&da)[6], const float (&db)[6],
+                                        const Taps3 &kU, const Taps3 &kG, bool first_col,
+                                        float (&m)[9])
+{
+    float u[9];
+    up_odd_row(xa, xb, kU, u);
+    if (kBwd) {
+        float g[9];
+        up_odd_row(da, db, kG, g);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) m[c] = gelu_erf_grad(u[c]) * g[c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) m[c] = gelu_erf(u[c]);
+    }
+    if (first_col) m[0] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------
+// row sources
+// ---------------------------------------------------------------------------------
+template <typename T, bool kRes>
+struct GlobalRows {
+    const T *x;   // plane base, already offset to column j
+    const T *r;   // residual plane (kRes), same offset
+    int H, W, j;
+    __device__ __forceinline__ void load(int row, float (&v)[6]) const
+    {
+        if (row < 0 || row >= H) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) v[c] = 0.f;
+            return;
+        }
+        const long off = (long)row * W;
+        float4 c4 = ld4(x + off);
+        float l = (j > 0) ? ld1(x + off - 1) : 0.f;
+        float rr = (j + 4 < W) ? ld1(x + off + 4) : 0.f;
+        if (kRes) {
+            float4 q4 = ld4(r + off);
+            c4.x += q4.x; c4.y += q4.y; c4.z += q4.z; c4.w += q4.w;
+            if (j > 0) l += ld1(r + off - 1);
+            if (j + 4 < W) rr += ld1(r + off + 4);
+        }
+        v[0] = l; v[1] = c4.x; v[2] = c4.y; v[3] = c4.z; v[4] = c4.w; v[5] = rr;
+    }
+};
+
+template <typename T, bool kRes>
+struct TileRows {
+    const T *x;   // shared tile, pointing at (tile row 0, this thread's column j)
+    const T *r;
+    int pitch, row0;   // row0 = global row index of tile row 0
+    __device__ __forceinline__ void load(int row, float (&v)[6]) const
+    {
+        const int off = (row - row0) * pitch;
+        float4 c4 = lds4(x + off);
+        float l = lds1(x + off - 1), rr = lds1(x + off + 4);
+        if (kRes) {
+            float4 q4 = lds4(r + off);
+            c4.x += q4.x; c4.y += q4.y; c4.z += q4.z; c4.w += q4.w;
+            l += lds1(r + off - 1); rr += lds1(r + off + 4);
+        }
+        v[0] = l; v[1] = c4.x; v[2] = c4.y; v[3] = c4.z; v[4] = c4.w; v[5] = rr;
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// the strip core
+// ---------------------------------------------------------------------------------
+template <bool kBwd, class SX, class SD, typename TO>
+__device__ __forceinline__ void strip_core(const SX &sx, const SD &sd, TO *__restrict__ out, int W,
+                                           int i0, int i1, bool first_col, const Taps3 &kU,
+                                           const Taps3 &kG, const Taps3 &kB)
+{
+    float xa[6], xb[6], da[6], db[6], gp[9];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { da[c] = 0.f; db[c] = 0.f; }
+    sx.load(i0, xb);
+    if (kBwd) sd.load(i0, db);
+    if (i0 > 0) {
+        sx.load(i0 - 1, xa);
+        if (kBwd) sd.load(i0 - 1, da);
+        mid_odd<kBwd>(xa, xb, da, db, kU, kG, first_col, gp);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) gp[c] = 0.f;
+    }
+    for (int i = i0; i < i1; ++i) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { xa[c] = xb[c]; da[c] = db[c]; }
+        sx.load(i + 1, xb);
+        if (kBwd) sd.load(i + 1, db);
+        float ge[9], go[9];
+        mid_even<kBwd>(xa, da, kU, kG, first_col, ge);
+        mid_odd<kBwd>(xa, xb, da, db, kU, kG, first_col, go);
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float acc = kB.k[0][0] * gp[2 * q];
+            acc = fmaf(kB.k[0][1], gp[2 * q + 1], acc);
+            acc = fmaf(kB.k[0][2], gp[2 * q + 2], acc);
+            acc = fmaf(kB.k[1][0], ge[2 * q], acc);
+            acc = fmaf(kB.k[1][1], ge[2 * q + 1], acc);
+            acc = fmaf(kB.k[1][2], ge[2 * q + 2], acc);
+            acc = fmaf(kB.k[2][0], go[2 * q], acc);
+            acc = fmaf(kB.k[2][1], go[2 * q + 1], acc);
+            acc = fmaf(kB.k[2][2], go[2 * q + 2], acc);
+            o[q] = acc;
+        }
+        st4(out + (long)i * W, make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+        for (int c = 0; c < 9; ++c) gp[c] = go[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// direct kernel
+// ---------------------------------------------------------------------------------
+template <typename T, bool kBwd, bool kRes>
+__global__ void __launch_bounds__(256)
+fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T *__restrict__ dy,
+                     T *__restrict__ out, long planes, int H, int W, int strips, int nseg, int R,
+                     const __grid_constant__ Taps3 kU, const __grid_constant__ Taps3 kG,
+                     const __grid_constant__ Taps3 kB)
+{
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long per_plane = (long)strips * nseg;
+    if (idx >= planes * per_plane) return;
+    const int s = (int)(idx % strips);
+    const int seg = (int)((idx / strips) % nseg);
+    const long p = idx / per_plane;
+    const int j = 4 * s, i0 = seg * R, i1 = min(H, i0 + R);
+    const long base = p * (long)H * W + j;
+    GlobalRows<T, kRes> sx{x + base, kRes ? res + base : nullptr, H, W, j};
+    GlobalRows<T, false> sd{kBwd ? dy + base : nullptr, nullptr, H, W, j};
+    strip_core<kBwd>(sx, sd, out + base, W, i0, i1, j == 0, kU, kG, kB);
+}
+
+// ---------------------------------------------------------------------------------
+// TMA-staged kernel
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+struct TileCfg {
+    int Tw, Th, P, R;          // tile width/height (outputs), planes per tile, rows per thread
+    int strips, nseg;          // Tw/4, Th/R
+    int tiles_x, tiles_y;
+    int tile_bytes;            // bytes of one staged tile, rounded up to 128
+};
+
+template <typename T, bool kBwd, bool kRes>
+__global__ void __launch_bounds__(256)
+fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mres,
+                  const __grid_constant__ CUtensorMap mdy, T *__restrict__ out, long planes, int H,
+                  int W, const __grid_constant__ TileCfg cfg, const __grid_constant__ Taps3 kU,
+                  const __grid_constant__ Taps3 kG, const __grid_constant__ Taps3 kB)
+{
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ __align__(8) uint64_t bar;
+
+    long bid = blockIdx.x;
+    const int tx = (int)(bid % cfg.tiles_x); bid /= cfg.tiles_x;
+    const int ty = (int)(bid % cfg.tiles_y);
+    const long p0 = (bid / cfg.tiles_y) * cfg.P;
+    const int j0 = tx * cfg.Tw, it0 = ty * cfg.Th;
+    const int pitch = cfg.Tw + 8, rows = cfg.Th + 2;
+
+    T *xs = reinterpret_cast<T *>(tile_smem);
+    T *rs = reinterpret_cast<T *>(tile_smem + (kRes ? cfg.tile_bytes : 0));
+    T *ds = reinterpret_cast<T *>(tile_smem + (kRes ? 2 : 1) * cfg.tile_bytes);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t box_bytes = (uint32_t)(pitch * rows * cfg.P * sizeof(T));
+        mbar_expect_tx(&bar, box_bytes * (1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0)));
+        tma_load_3d(xs, &mx, &bar, j0 - 4, it0 - 1, (int)p0);
+        if (kRes) tma_load_3d(rs, &mres, &bar, j0 - 4, it0 - 1, (int)p0);
+        if (kBwd) tma_load_3d(ds, &mdy, &bar, j0 - 4, it0 - 1, (int)p0);
+    }
+
+    const int s = threadIdx.x % cfg.strips;
+    const int q = threadIdx.x / cfg.strips;
+    const int pl = q % cfg.P, seg = q / cfg.P;
+    const long p = p0 + pl;
+    const int j = j0 + 4 * s;
+    const int i0 = it0 + seg * cfg.R;
+    const int i1 = min(min(H, it0 + cfg.Th), i0 + cfg.R);
+    const bool active = (seg < cfg.nseg) && (p < planes) && (j < W) && (i0 < i1);
+
+    mbar_wait(&bar, 0);
+    if (!active) return;
+
+    const int toff = pl * rows * pitch + 4 + 4 * s;
+    TileRows<T, kRes> sx{xs + toff, rs + toff, pitch, it0 - 1};
+    TileRows<T, false> sd{ds + toff, nullptr, pitch, it0 - 1};
+    strip_core<kBwd>(sx, sd, out + p * (long)H * W + j, W, i0, i1, j == 0, kU, kG, kB);
+}
+
+// ---------------------------------------------------------------------------------
+// standalone N == 3 resamplers (HBM-bound)
+// ---------------------------------------------------------------------------------
+// up-like: thread = 4 input columns -> 8 output columns, two output rows per input row
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+up3_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int H, int W, int strips,
+           int nseg, int R, const __grid_constant__ Taps3 k)
+{
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long per_plane = (long)strips * nseg;
+    if (idx >= planes * per_plane) return;
+    const int s = (int)(idx % strips);
+    const int seg = (int)((idx / strips) % nseg);
+    const long p = idx / per_plane;
+    const int j = 4 * s, i0 = seg * R, i1 = min(H, i0 + R);
+    const TI *src = in + p * (long)H * W + j;
+    TO *dst = out + p * 4L * H * W + 2 * j;
+    const int W2 = 2 * W;
+    const bool has_r = (j + 4 < W);
+
+    float xa[5], xb[5];
+    {
+        float4 c = ld4(src + (long)i0 * W);
+        xb[0] = c.x; xb[1] = c.y; xb[2] = c.z; xb[3] = c.w;
+        xb[4] = has_r ? ld1(src + (long)i0 * W + 4) : 0.f;
+    }
+    for (int i = i0; i < i1; ++i) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) xa[c] = xb[c];
+        if (i + 1 < H) {
+            float4 c = ld4(src + (long)(i + 1) * W);
+            xb[0] = c.x; xb[1] = c.y; xb[2] = c.z; xb[3] = c.w;
+            xb[4] = has_r ? ld1(src + (long)(i + 1) * W + 4) : 0.f;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) xb[c] = 0.f;
+        }
+        float e[8], o[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            e[2 * c] = k.k[1][1] * xa[c];
+            e[2 * c + 1] = fmaf(k.k[1][2], xa[c + 1], k.k[1][0] * xa[c]);
+            o[2 * c] = fmaf(k.k[2][1], xb[c], k.k[0][1] * xa[c]);
+            float t = k.k[0][0] * xa[c];
+            t = fmaf(k.k[0][2], xa[c + 1], t);
+            t = fmaf(k.k[2][0], xb[c], t);
+            o[2 * c + 1] = fmaf(k.k[2][2], xb[c + 1], t);
+        }
+        TO *r0 = dst + (long)(2 * i) * W2;
+        st4(r0, make_float4(e[0], e[1], e[2], e[3]));
+        st4(r0 + 4, make_float4(e[4], e[5], e[6], e[7]));
+        st4(r0 + W2, make_float4(o[0], o[1], o[2], o[3]));
+        st4(r0 + W2 + 4, make_float4(o[4], o[5], o[6], o[7]));
+    }
+}
+
+// down-like: thread = 4 output columns; input rows 2i-1, 2i, 2i+1, columns 2j-1 .. 2j+7
+template <typename T>
+__device__ __forceinline__ void load9(const T *plane, int row, int H, int W, int c0, bool has_l,
+                                      float (&v)[9])
+{
+    if (row < 0 || row >= H) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) v[c] = 0.f;
+        return;
+    }
+    const T *p = plane + (long)row * W + c0;
+    float4 a = ld4(p), b = ld4(p + 4);
+    v[0] = has_l ? ld1(p - 1) : 0.f;
+    v[1] = a.x; v[2] = a.y; v[3] = a.z; v[4] = a.w;
+    v[5] = b.x; v[6] = b.y; v[7] = b.z; v[8] = b.w;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+down3_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, int W, int Ho,
+             int Wo, int strips, int nseg, int R, const __grid_constant__ Taps3 k)
+{
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long per_plane = (long)strips * nseg;
+    if (idx >= planes * per_plane) return;
+    const int s = (int)(idx % strips);
+    const int seg = (int)((idx / strips) % nseg);
+    const long p = idx / per_plane;
+    const int j = 4 * s, i0 = seg * R, i1 = min(Ho, i0 + R);
+    const T *plane = in + p * (long)H * W;
+    T *dst = out + p * (long)Ho * Wo + j;
+    const bool has_l = (j > 0);
+
+    float vp[9], ve[9], vo[9];
+    load9(plane, 2 * i0 - 1, H, W, 2 * j, has_l, vp);
+    for (int i = i0; i < i1; ++i) {
+        load9(plane, 2 * i, H, W, 2 * j, has_l, ve);
+        load9(plane, 2 * i + 1, H, W, 2 * j, has_l, vo);
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float acc = k.k[0][0] * vp[2 * q];
+            acc = fmaf(k.k[0][1], vp[2 * q + 1], acc);
+            acc = fmaf(k.k[0][2], vp[2 * q + 2], acc);
+            acc = fmaf(k.k[1][0], ve[2 * q], acc);
+            acc = fmaf(k.k[1][1], ve[2 * q + 1], acc);
+            acc = fmaf(k.k[1][2], ve[2 * q + 2], acc);
+            acc = fmaf(k.k[2][0], vo[2 * q], acc);
+            acc = fmaf(k.k[2][1], vo[2 * q + 1], acc);
+            acc = fmaf(k.k[2][2], vo[2 * q + 2], acc);
+            o[q] = acc;
+        }
+        st4(dst + (long)i * Wo, make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+        for (int c = 0; c < 9; ++c) vp[c] = vo[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+static inline bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+static inline size_t esize(int dtype) { return dtype == AFR_F32 ? 4 : 2; }
+
+bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype)
+{
+    if (H < 1 || W < 4 || (W % 4) != 0) return false;
+    for (int i = 0; i < nptrs; ++i)
+        if (ptrs[i] && !aligned_to(ptrs[i], 4 * esize(dtype))) return false;
+    return true;
+}
+
+bool n3_fgelu_tma_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype)
+{
+    if (!n3_fgelu_supported(H, W, ptrs, nptrs, dtype)) return false;
+    if (H < 16 || W < 16) return false;                       // tiny planes: direct path
+    if ((W * esize(dtype)) % 16 != 0) return false;           // TMA global strides
+    for (int i = 0; i < nptrs - 1; ++i)                       // inputs only (last ptr = output)
+        if (ptrs[i] && !aligned_to(ptrs[i], 16)) return false;
+    return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) !=
+                cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(sym);
+    }();
+    return fn;
+}
+
+static bool make_plane_map(CUtensorMap *m, const void *base, long planes, int H, int W, int dtype,
+                           int box_w, int box_h, int box_p)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const size_t es = esize(dtype);
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)W * es, (cuuint64_t)W * H * es};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_p};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, dtype == AFR_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                     3, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static inline int pick_rows(int H) { return H < 8 ? H : 8; }
+
+template <typename T, bool kBwd, bool kRes>
+static cudaError_t launch_direct(const void *x, const void *res, const void *dy, void *out,
+                                 long planes, int H, int W, const Taps3 &kU, const Taps3 &kG,
+                                 const Taps3 &kB, cudaStream_t s)
+{
+    const int strips = W / 4, R = pick_rows(H), nseg = (H + R - 1) / R;
+    const long total = planes * (long)strips * nseg;
+    const int block = 128;
+    const long grid = (total + block - 1) / block;
+    if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    fgelu3_direct_kernel<T, kBwd, kRes><<<(unsigned)grid, block, 0, s>>>(
+        (const T *)x, (const T *)res, (const T *)dy, (T *)out, planes, H, W, strips, nseg, R, kU, kG, kB);
+    return cudaGetLastError();
+}
+
+static bool pick_tile(int H, int W, int dtype, int ntiles, int *threads, TileCfg *cfg)
+{
+    const size_t es = esize(dtype);
+    for (int th = 256; th >= 64; th /= 2) {
+        TileCfg c;
+        c.Tw = W <= 128 ? W : 128;
+        c.strips = c.Tw / 4;
+        c.R = pick_rows(H);
+        const int q = th / c.strips;
+        if (q < 1) continue;
+        const int nseg_total = (H + c.R - 1) / c.R;
+        c.nseg = nseg_total < q ? nseg_total : q;
+        c.P = q / c.nseg;
+        c.Th = c.nseg * c.R;
+        c.tiles_x = (W + c.Tw - 1) / c.Tw;
+        c.tiles_y = (H + c.Th - 1) / c.Th;
+        size_t bytes = (size_t)(c.Tw + 8) * (c.Th + 2) * c.P * es;
+        c.tile_bytes = (int)((bytes + 127) / 128 * 128);
+        if (c.P > 256 || c.Th + 2 > 256) continue;
+        if ((size_t)c.tile_bytes * ntiles <= 48 * 1024 || th == 64) {
+            if ((size_t)c.tile_bytes * ntiles > 200 * 1024) return false;
+            *threads = th; *cfg = c;
+            return true;
+        }
+    }
+    return false;
+}
+
+template <typename T, bool kBwd, bool kRes>
+static cudaError_t launch_tma(const void *x, const void *res, const void *dy, void *out,
+                              long planes, int H, int W, int dtype, const Taps3 &kU,
+                              const Taps3 &kG, const Taps3 &kB, cudaStream_t s)
+{
+    const int ntiles = 1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0);
+    int threads; TileCfg cfg;
+    if (!pick_tile(H, W, dtype, ntiles, &threads, &cfg)) return cudaErrorInvalidConfiguration;
+    CUtensorMap mx, mres, mdy;
+    if (!make_plane_map(&mx, x, planes, H, W, dtype, cfg.Tw + 8, cfg.Th + 2, cfg.P)) return cudaErrorNotSupported;
+    mres = mx; mdy = mx;
+    if (kRes && !make_plane_map(&mres, res, planes, H, W, dtype, cfg.Tw + 8, cfg.Th + 2, cfg.P)) return cudaErrorNotSupported;
+    if (kBwd && !make_plane_map(&mdy, dy, planes, H, W, dtype, cfg.Tw + 8, cfg.Th + 2, cfg.P)) return cudaErrorNotSupported;
+    const long pgroups = (planes + cfg.P - 1) / cfg.P;
+    const long grid = pgroups * cfg.tiles_x * cfg.tiles_y;
+    if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    const size_t smem = (size_t)cfg.tile_bytes * ntiles;
+    auto kern = fgelu3_tma_kernel<T, kBwd, kRes>;
+    static bool attr_set = false;     // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    kern<<<(unsigned)grid, threads, smem, s>>>(mx, mres, mdy, (T *)out, planes, H, W, cfg, kU, kG, kB);
+    return cudaGetLastError();
+}
+
+cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, void *out, long planes, int H,
+                     int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd, int dtype,
+                     bool use_tma, cudaStream_t s, const char **kernel_name)
+{
+#define AFR_GO(T, B, R)                                                                           \
+    return use_tma ? launch_tma<T, B, R>(x, res, dy, out, planes, H, W, dtype, kU, kG, kB, s)     \
+                   : launch_direct<T, B, R>(x, res, dy, out, planes, H, W, kU, kG, kB, s)
+    if (kernel_name) *kernel_name = use_tma ? "fgelu3_tma_kernel" : "fgelu3_direct_kernel";
+    if (dtype == AFR_F32) {
+        if (bwd) { if (res) { AFR_GO(float, true, true); } else { AFR_GO(float, true, false); } }
+        else     { if (res) { AFR_GO(float, false, true); } else { AFR_GO(float, false, false); } }
+    } else {
+        if (bwd) { if (res) { AFR_GO(bf16, true, true); } else { AFR_GO(bf16, true, false); } }
+        else     { if (res) { AFR_GO(bf16, false, true); } else { AFR_GO(bf16, false, false); } }
+    }
+#undef AFR_GO
+}
+
+bool n3_up_supported(int H, int W, const void *in, const void *out, int in_dtype, int out_dtype)
+{
+    return H >= 1 && W >= 4 && (W % 4) == 0 && aligned_to(in, 4 * esize(in_dtype)) &&
+           aligned_to(out, 4 * esize(out_dtype));
+}
+
+cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,
+                       int in_dtype, int out_dtype, cudaStream_t s)
+{
+    const int strips = W / 4, R = pick_rows(H), nseg = (H + R - 1) / R;
+    const long total = planes * (long)strips * nseg;
+    const long grid = (total + 255) / 256;
+    if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+#define AFR_UP(TI, TO)                                                                        \
+    up3_kernel<TI, TO><<<(unsigned)grid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, H, W, \
+                                                      strips, nseg, R, k)
+    if (in_dtype == AFR_F32 && out_dtype == AFR_F32) AFR_UP(float, float);
+    else if (in_dtype == AFR_BF16 && out_dtype == AFR_BF16) AFR_UP(bf16, bf16);
+    else if (in_dtype == AFR_BF16 && out_dtype == AFR_F32) AFR_UP(bf16, float);
+    else AFR_UP(float, bf16);
+#undef AFR_UP
+    return cudaGetLastError();
+}
+
+bool n3_down_supported(int H, int W, const void *in, const void *out, int dtype)
+{
+    return H >= 1 && W >= 8 && (W % 8) == 0 && aligned_to(in, 4 * esize(dtype)) &&
+           aligned_to(out, 4 * esize(dtype));
+}
+
+cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,
+                         int dtype, cudaStream_t s)
+{
+    const int Ho = (H + 1) / 2, Wo = W / 2;
+    const int strips = Wo / 4, R = pick_rows(Ho), nseg = (Ho + R - 1) / R;
+    const long total = planes * (long)strips * nseg;
+    const long grid = (total + 255) / 256;
+    if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    if (dtype == AFR_F32)
+        down3_kernel<float><<<(unsigned)grid, 256, 0, s>>>((const float *)in, (float *)out, planes,
+                                                           H, W, Ho, Wo, strips, nseg, R, k);
+    else
+        down3_kernel<bf16><<<(unsigned)grid, 256, 0, s>>>((const bf16 *)in, (bf16 *)out, planes, H,
+                                                          W, Ho, Wo, strips, nseg, R, k);
+    return cudaGetLastError();
+}
+
+}  // namespace afr

@@ -1,0 +1,134 @@
+"""DDPM process of the reference (modules/ddpm_models.py:301-436) with the sampler kept on
+the device.
+
+``Diffusion`` has the reference's constructor and methods (noise_images, sample_timesteps,
+sample, revert, rotate_2d_matrix, sample_shift).  Differences, all invisible in the results:
+  * the Config-E rotation (``theta``) runs as a CUDA kernel instead of
+    device -> host -> scipy.ndimage.rotate -> device on each of the 999 steps;
+  * the posterior update of Algorithm 1 (:374) is one fused kernel; its three scalar
+    coefficients come from a host-side table computed with the reference's fp32 op order;
+  * no per-step host tensors are created (the reference builds ``t`` on the CPU each step, :362).
+"""
+import logging
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+class Diffusion:
+    def __init__(self, noise_steps=1000, beta_start=1e-4, beta_end=0.02, img_size=256, device="cuda"):
+        self.noise_steps, self.beta_start, self.beta_end = noise_steps, beta_start, beta_end
+        self.img_size, self.device = img_size, device
+        self.beta = self.prepare_noise_schedule().to(device)
+        self.alpha = 1.0 - self.beta
+        self.alpha_hat = torch.cumprod(self.alpha, dim=0)
+        self.filter = None
+        # host tables of the per-step scalars of ddpm_models.py:374, same fp32 op order
+        a, ah, b = self.alpha.cpu(), self.alpha_hat.cpu(), self.beta.cpu()
+        self._ca = (1 / torch.sqrt(a)).tolist()
+        self._cb = ((1 - a) / torch.sqrt(1 - ah)).tolist()
+        self._cc = torch.sqrt(b).tolist()
+
+    def prepare_noise_schedule(self):
+        return torch.linspace(self.beta_start, self.beta_end, self.noise_steps)
+
+    def noise_images(self, x, t, generator=None):
+        """q-sample (ddpm_models.py:317-321)."""
+        sa = torch.sqrt(self.alpha_hat[t])[:, None, None, None]
+        sb = torch.sqrt(1 - self.alpha_hat[t])[:, None, None, None]
+        eps = torch.randn(x.shape, dtype=x.dtype, device=x.device, generator=generator) \
+            if generator is not None else torch.randn_like(x)
+        return sa * x + sb * eps, eps
+
+    def sample_timesteps(self, n, generator=None):
+        return torch.randint(low=1, high=self.noise_steps, size=(n,), generator=generator)
+
+    # -- Algorithm 1 --------------------------------------------------------------------
+    def _initial(self, n, image_channels, x_init, generator):
+        if x_init is not None:
+            return x_init.to(self.device, torch.float32).contiguous().clone()
+        shape = (n, image_channels, self.img_size, self.img_size)
+        # the reference draws the start noise on the CPU generator, then moves it (:360)
+        return torch.randn(shape, generator=generator).to(self.device).contiguous()
+
+    def _reverse_step(self, model, x, i, noise):
+        t = torch.full((x.shape[0],), i, dtype=torch.long, device=x.device)
+        eps = model(x, t).float().contiguous()
+        ops.ddpm_update_(x, eps, noise, self._ca[i], self._cb[i], self._cc[i])
+        return x
+
+    def _loop(self, model, n, image_channels, theta, keep, x_init, generator, noise_source, progress):
+        theta_step = None if theta is None else theta / self.noise_steps
+        x = self._initial(n, image_channels, x_init, generator)
+        kept = []
+        steps = reversed(range(1, self.noise_steps))
+        if progress:
+            from tqdm import tqdm
+            steps = tqdm(steps, position=0, total=self.noise_steps - 1)
+        for i in steps:
+            noise = None
+            if i > 1:
+                noise = noise_source(x) if noise_source is not None else torch.randn_like(x)
+            x = self._reverse_step(model, x, i, noise)
+            if theta_step is not None:
+                x = ops.rotate(x, theta_step)
+            if keep and i % 100 == 0:
+                kept.append(x.clone())
+        return x, kept
+
+    @staticmethod
+    def _to_u8(x):
+        return (((x.clamp(-1, 1) + 1) / 2) * 255).type(torch.uint8)
+
+    def sample(self, model, n, image_channels, theta=None, x_init=None, generator=None,
+               noise_source=None, progress=False, return_float=False):
+        """Ancestral sampling, ddpm_models.py:352-386.  Returns ``(x_u8, result_u8)`` like the
+        reference (``result`` = snapshots every 100 steps + the final x).  ``noise_source(x)``
+        lets a caller inject the per-step noise (tests replay the reference's CPU stream;
+        the sharded sampler slices a full-batch stream)."""
+        logging.info(f"Sampling {n} new images....")
+        model.eval()
+        with torch.no_grad():
+            x, kept = self._loop(model, n, image_channels, theta, True, x_init, generator,
+                                 noise_source, progress)
+        model.train()                       # the reference unconditionally does (:379)
+        kept.append(x)
+        if return_float:
+            return x, torch.cat(kept)
+        return self._to_u8(x), self._to_u8(torch.cat(kept))
+
+    def revert(self, model, n, image_channels, **kw):
+        """ddpm_models.py:326-350: like ``sample`` without rotation, returns only the snapshots."""
+        return self.sample(model, n, image_channels, theta=None, **kw)[1]
+
+    def sample_shift(self, model, n, image_channels, shift=None, **kw):
+        """Translation variant (ddpm_models.py:388-419, 'under development' upstream): a
+        1-pixel horizontal grid-wrap roll at evenly spaced steps -- ``torch.roll`` on device."""
+        if shift == 0:
+            shift = None
+        idx = set()
+        if shift is not None:
+            dur = np.abs(shift) / self.noise_steps
+            idx = set(np.round(np.arange(0, self.noise_steps, dur)).astype(int)[1:].tolist())
+        model.eval()
+        with torch.no_grad():
+            x = self._initial(n, image_channels, kw.get("x_init"), kw.get("generator"))
+            for i in reversed(range(1, self.noise_steps)):
+                noise = torch.randn_like(x) if i > 1 else None
+                x = self._reverse_step(model, x, i, noise)
+                if shift is not None and i in idx:
+                    x = torch.roll(x, int(np.sign(shift)), dims=3)
+        model.train()
+        return self._to_u8(x)
+
+    @staticmethod
+    def rotate_2d_matrix(matrix, degrees, filter=None):
+        """ddpm_models.py:421-429, on device."""
+        return ops.rotate(matrix, degrees)
+
+    @staticmethod
+    def shift_2d_matrix(matrix, hshift, vshift, device=None):
+        """ddpm_models.py:431-436 (integer grid-wrap shift)."""
+        return torch.roll(matrix, (int(vshift), int(hshift)), dims=(2, 3))

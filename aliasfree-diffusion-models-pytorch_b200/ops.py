@@ -1,0 +1,226 @@
+"""PyTorch-facing operators of the alias-free resampling path.
+
+Thin host code: argument checks, output allocation and ``torch.autograd.Function``
+wrappers around the C ABI of ``libafr_b200.so`` (include/afr.h).  All compute happens in
+the CUDA kernels; a non-CUDA tensor is an error (there is no CPU fallback).
+
+Names mirror the reference: ``custom_upsample`` / ``custom_downsample`` have the
+signatures of modules/filtrs.py:79 and :71.
+"""
+import ctypes
+
+import torch
+
+from . import _native
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _check(rc):
+    if rc != 0:
+        L = _native.lib()
+        raise RuntimeError("afr: %s: %s" % (L.afr_status_string(rc).decode(), L.afr_last_error().decode()))
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require(x, name="x"):
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("afr: %s must be a torch.Tensor" % name)
+    if not x.is_cuda:
+        raise RuntimeError("afr: %s must be a CUDA tensor (this build has no CPU fallback)" % name)
+    if x.dim() != 4:
+        raise ValueError("afr: %s must be [B, C, H, W], got %s" % (name, tuple(x.shape)))
+    if x.dtype not in _DT:
+        raise TypeError("afr: %s dtype %s unsupported (float32 / bfloat16)" % (name, x.dtype))
+    return x.contiguous()
+
+
+class Taps:
+    """Host copy of an N x N filter, kept alive next to its ctypes pointer."""
+    __slots__ = ("t", "n", "ptr")
+
+    def __init__(self, filt):
+        if isinstance(filt, Taps):
+            self.t, self.n, self.ptr = filt.t, filt.n, filt.ptr
+            return
+        t = torch.as_tensor(filt).detach().to("cpu", torch.float32).contiguous()
+        if t.dim() != 2 or t.shape[0] != t.shape[1]:
+            raise ValueError("afr: filter must be N x N, got %s" % (tuple(t.shape),))
+        self.t, self.n, self.ptr = t, int(t.shape[0]), ctypes.c_void_p(t.data_ptr())
+
+
+def _taps(filt):
+    return filt if isinstance(filt, Taps) else Taps(filt)
+
+
+# ---- raw launches (no autograd) ---------------------------------------------------
+def _up_fwd(x, k, out_dtype):
+    B, C, H, W = x.shape
+    u = torch.empty((B, C, 2 * H, 2 * W), dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(_native.lib().afr_up2x_fwd(x.data_ptr(), u.data_ptr(), B, C, H, W, k.ptr, k.n,
+                                          _DT[x.dtype], _DT[out_dtype], _stream(x)))
+    return u
+
+
+def _up_bwd(du, k, H, W):
+    B, C = du.shape[:2]
+    dx = torch.empty((B, C, H, W), dtype=du.dtype, device=du.device)
+    with torch.cuda.device(du.device):
+        _check(_native.lib().afr_up2x_bwd(du.data_ptr(), dx.data_ptr(), B, C, H, W, k.ptr, k.n,
+                                          _DT[du.dtype], _DT[dx.dtype], _stream(du)))
+    return dx
+
+
+def _down_fwd(v, k):
+    B, C, H, W = v.shape
+    y = torch.empty((B, C, (H + 1) // 2, (W + 1) // 2), dtype=v.dtype, device=v.device)
+    with torch.cuda.device(v.device):
+        _check(_native.lib().afr_down2x_fwd(v.data_ptr(), y.data_ptr(), B, C, H, W, k.ptr, k.n,
+                                            _DT[v.dtype], _stream(v)))
+    return y
+
+
+def _down_bwd(dy, k, H, W):
+    B, C = dy.shape[:2]
+    dv = torch.empty((B, C, H, W), dtype=dy.dtype, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _check(_native.lib().afr_down2x_bwd(dy.data_ptr(), dv.data_ptr(), B, C, H, W, k.ptr, k.n,
+                                            _DT[dy.dtype], _stream(dy)))
+    return dv
+
+
+def _fgelu_fwd(x, res, ku, kd):
+    B, C, H, W = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _check(_native.lib().afr_filtered_gelu_fwd(
+            x.data_ptr(), None if res is None else res.data_ptr(), y.data_ptr(), B, C, H, W,
+            ku.ptr, ku.n, kd.ptr, kd.n, _DT[x.dtype], _stream(x)))
+    return y
+
+
+def _fgelu_bwd(x, res, dy, ku, kd):
+    B, C, H, W = x.shape
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _check(_native.lib().afr_filtered_gelu_bwd(
+            x.data_ptr(), None if res is None else res.data_ptr(), dy.data_ptr(), dx.data_ptr(),
+            B, C, H, W, ku.ptr, ku.n, kd.ptr, kd.n, _DT[x.dtype], _stream(x)))
+    return dx
+
+
+# ---- autograd -------------------------------------------------------------------------
+class _Up2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, out_dtype):
+        ctx.k, ctx.hw, ctx.in_dtype = k, tuple(x.shape[-2:]), x.dtype
+        return _up_fwd(x, k, out_dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, du):
+        dx = _up_bwd(du.contiguous(), ctx.k, *ctx.hw)
+        return dx.to(ctx.in_dtype), None, None
+
+
+class _Down2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, k):
+        ctx.k, ctx.hw = k, tuple(v.shape[-2:])
+        return _down_fwd(v, k)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        return _down_bwd(dy.contiguous(), ctx.k, *ctx.hw), None
+
+
+class _FilteredGelu(torch.autograd.Function):
+    """Saves only x (and the residual): u, gelu(u) and their 4x-sized gradients are
+    recomputed inside the backward kernel."""
+
+    @staticmethod
+    def forward(ctx, x, res, ku, kd):
+        ctx.ku, ctx.kd = ku, kd
+        ctx.has_res = res is not None
+        if ctx.has_res:
+            ctx.save_for_backward(x, res)
+        else:
+            ctx.save_for_backward(x)
+        return _fgelu_fwd(x, res, ku, kd)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        saved = ctx.saved_tensors
+        x, res = saved[0], (saved[1] if ctx.has_res else None)
+        dx = _fgelu_bwd(x, res, dy.contiguous().to(x.dtype), ctx.ku, ctx.kd)
+        return dx, (dx if ctx.has_res else None), None, None
+
+
+# ---- public functions -----------------------------------------------------------------
+def up2x(x, filt, out_dtype=None):
+    """Zero-stuff x2 + depthwise N x N low-pass, 'same' zero padding, no gain."""
+    x = _require(x)
+    return _Up2x.apply(x, _taps(filt), out_dtype or x.dtype)
+
+
+def down2x(x, filt):
+    """Depthwise N x N low-pass then keep every 2nd row/column; output is contiguous."""
+    return _Down2x.apply(_require(x), _taps(filt))
+
+
+def filtered_gelu(x, filt_up, filt_down, residual=None):
+    """down2x(gelu(up2x(x + residual, filt_up)), filt_down) in ONE kernel (exact erf GELU).
+    Replaces modules/ddpm_utils.py:123-125 / 128-131 / 137-139."""
+    x = _require(x)
+    if residual is not None:
+        residual = _require(residual, "residual")
+        if residual.shape != x.shape or residual.dtype != x.dtype:
+            raise ValueError("afr: residual must match x in shape and dtype")
+    return _FilteredGelu.apply(x, residual, _taps(filt_up), _taps(filt_down))
+
+
+def custom_upsample(x, sinc_filter, factor=2):
+    """Signature of modules/filtrs.py:79.  Like the reference, the result is float32
+    whatever the input dtype (filtrs.py:85 allocates an fp32 buffer)."""
+    if factor != 2:
+        raise NotImplementedError("afr: only factor=2 is implemented (every reference call site uses 2)")
+    return up2x(x, sinc_filter, out_dtype=torch.float32)
+
+
+def custom_downsample(x, jinc_filter, factor=2):
+    """Signature of modules/filtrs.py:71."""
+    if factor != 2:
+        raise NotImplementedError("afr: only factor=2 is implemented (every reference call site uses 2)")
+    return down2x(x, jinc_filter)
+
+
+def rotate(x, degrees):
+    """scipy.ndimage.rotate(x, degrees, axes=(2,3), reshape=False, mode='grid-wrap') on device
+    (modules/ddpm_models.py:421-429).  No autograd (the sampler runs under no_grad)."""
+    x = _require(x)
+    if x.dtype != torch.float32:
+        raise TypeError("afr: rotate needs float32")
+    B, C, H, W = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _check(_native.lib().afr_rotate_periodic_cubic(x.data_ptr(), y.data_ptr(), B, C, H, W,
+                                                       float(degrees), 0, _stream(x)))
+    return y
+
+
+def ddpm_update_(x, eps, noise, ca, cb, cc):
+    """In place  x <- ca * (x - cb * eps) + cc * noise  (modules/ddpm_models.py:374)."""
+    for t in (x, eps) + (() if noise is None else (noise,)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError("afr: ddpm_update_ needs contiguous float32 CUDA tensors")
+    with torch.cuda.device(x.device):
+        _check(_native.lib().afr_ddpm_update(x.data_ptr(), eps.data_ptr(),
+                                             None if noise is None else noise.data_ptr(),
+                                             x.numel(), float(ca), float(cb), float(cc), _stream(x)))
+    return x

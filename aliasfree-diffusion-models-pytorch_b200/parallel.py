@@ -1,0 +1,122 @@
+"""Multi-GPU use of the path: one process per GPU, ``torch.distributed`` for plumbing.
+
+* Sampling shards the image batch across ranks with NO communication during the 999-step
+  loop (every image is independent: GroupNorm(1, C) and attention are per-sample); an
+  optional final ``all_gather`` collects the uint8 images (4096 x 3 x 32 x 32 = 12.6 MB).
+* Training is data parallel with ONE NCCL all-reduce per step over a flat gradient buffer
+  (5.9 M fp32 = 23.6 MB), issued after backward.  The reference has no distributed code
+  (SURVEY.md section 2); both wrappers are new code around its unchanged inner loops
+  (modules/ddpm_models.py:359-378 and modules/ddpm_utils.py:498-509).
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n, rank, world_size):
+    """Contiguous, balanced split of ``n`` items: first ``n % world`` ranks get one extra."""
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class ShardedNoise:
+    """Per-step noise source that reproduces an UNSHARDED run bit for bit: every rank draws
+    the full-batch tensor from an identically seeded generator and keeps its slice
+    (50 MB/step at n=4096 -- cheap next to a UNet forward)."""
+
+    def __init__(self, full_shape, lo, hi, device, seed):
+        self.shape, self.lo, self.hi = tuple(full_shape), lo, hi
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed)
+        self.device = device
+
+    def __call__(self, x):
+        full = torch.randn(self.shape, device=self.device, generator=self.gen)
+        return full[self.lo:self.hi].contiguous()
+
+
+def sharded_sample(diffusion, model, n, image_channels, theta=None, seed=0, gather=False,
+                   exact_stream=True, progress=False):
+    """Batch-sharded Algorithm 1.  Rank r samples images [lo, hi) of the global batch ``n``.
+    The start noise is the slice of the seeded CPU draw the unsharded reference would make
+    (modules/ddpm_models.py:360).  Returns this rank's ``(x_u8, result_u8)``; with
+    ``gather=True`` rank-ordered full tensors on every rank (equal shard sizes required)."""
+    rank, ws = world()
+    lo, hi = shard_bounds(n, rank, ws)
+    g = torch.Generator()
+    g.manual_seed(seed)
+    S = diffusion.img_size
+    x0 = torch.randn((n, image_channels, S, S), generator=g)[lo:hi]
+    noise = None
+    if exact_stream:
+        noise = ShardedNoise((n, image_channels, S, S), lo, hi, diffusion.device, seed + 1)
+    x, result = diffusion.sample(model, hi - lo, image_channels, theta=theta, x_init=x0,
+                                 noise_source=noise, progress=progress)
+    if gather and ws > 1:
+        if n % ws:
+            raise ValueError("gather=True needs n divisible by the world size")
+        xs = [torch.empty_like(x) for _ in range(ws)]
+        dist.all_gather(xs, x)
+        x = torch.cat(xs)
+        k = result.shape[0] // (hi - lo)
+        rs = [torch.empty_like(result) for _ in range(ws)]
+        dist.all_gather(rs, result)
+        # result is [k snapshots x shard]; re-interleave to [k x n]
+        result = torch.cat([torch.cat([r.view(k, hi - lo, *r.shape[1:])[s] for r in rs]) for s in range(k)])
+    return x, result
+
+
+class FlatGradAllReduce:
+    """Data-parallel wrapper: parameters broadcast from rank 0 once, then after every
+    backward ONE all-reduce (mean) over a single flat fp32 gradient buffer whose views are
+    the parameters' ``.grad`` tensors (no per-step packing copies)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        rank, ws = world()
+        self.world_size = ws
+        if ws > 1:
+            for t in list(model.parameters()) + list(model.buffers()):
+                dist.broadcast(t.data, src=0)
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_grad(self):
+        self.flat.zero_()
+
+    def sync(self):
+        """Average gradients across ranks: the single collective of a training step."""
+        if self.world_size > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(self.world_size)
+
+
+def train_step(model, diffusion, optimizer, images, ddp=None, generator=None):
+    """Inner step of the reference ``train`` (modules/ddpm_utils.py:498-509): timesteps,
+    q-sample, forward, MSE, backward, [grad all-reduce], AdamW.  Returns the loss tensor
+    (no host sync here; the reference's two ``loss.item()`` calls are the caller's business)."""
+    t = diffusion.sample_timesteps(images.shape[0], generator=generator).to(images.device)
+    x_t, noise = diffusion.noise_images(images, t)
+    pred = model(x_t, t)
+    loss = torch.nn.functional.mse_loss(pred, noise)
+    if ddp is not None:
+        ddp.zero_grad()
+    else:
+        optimizer.zero_grad(set_to_none=False)
+    loss.backward()
+    if ddp is not None:
+        ddp.sync()
+    optimizer.step()
+    return loss

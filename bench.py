@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the alias-free resampling hot path on B200 (contract: see DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference [...]                          the CPU path (oracle port), rank 0 only
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  Headline metric: algorithmic GB/s of the fused
+filtered nonlinearity (up2x -> GELU -> low-pass -> down2x, forward) on the BASELINE.json
+configs[4] microbench tensor, fp32, one batch per rank (weak scaling, no collective on
+the data path).  Extra keys: `roofline` (dominant kernel, timed live with CUDA events),
+`cpu_baseline` (oracle port on the host cores, bounded sample), `e2e` (same call through
+host buffers incl. H2D/D2H), `sweep` (other ops / dtypes / shapes) and `ddpm_v3`
+(Config-D reverse-diffusion steps: samples/sec at batch 4096 sharded over the ranks).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "alias_free_resample_GBps"
+UNIT = "GB/s"
+# configs[4] microbench tensor: 128 channels, 64x64 planes; B chosen so that x is 512 MiB
+# (input and output are each 4x the 126 MB L2, so nothing is served from cache between steps)
+WORKLOAD = dict(B=256, C=128, H=64, W=64)
+FS = dict(kernel_size=3, kaiser_beta=2, omega_c_down=np.pi / 2, omega_c_up=np.pi / 2)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if ws > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, ws, local
+
+
+def barrier(ws):
+    if ws > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(v, ws):
+    if ws == 1:
+        return v
+    import torch.distributed as dist
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_loop(fn, steps, warmup, ws, per_step_events=False):
+    """W untimed steps, then exactly K timed steps bracketed by barrier + synchronize.
+    Returns (total_ms max over ranks, [per-step ms] on this rank)."""
+    for _ in range(warmup):
+        fn()
+    barrier(ws)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for a, b in ev:
+        if per_step_events:
+            a.record()
+        fn()
+        if per_step_events:
+            b.record()
+    t1.record()
+    barrier(ws)
+    total = max_over_ranks(t0.elapsed_time(t1), ws)
+    per = [a.elapsed_time(b) for a, b in ev] if per_step_events else []
+    return total, per
+
+
+# ---- reference arm: the CPU path on the host cores ----------------------------------------
+def cpu_reference(sample_b, min_seconds=10.0, max_reps=50):
+    from oracle import oracle as o
+    o.build()
+    k = o.lowpass_taps(np.pi / 2, 3, 2.0)
+    C, H, W = WORKLOAD["C"], WORKLOAD["H"], WORKLOAD["W"]
+    x = np.random.default_rng(0).standard_normal((sample_b, C, H, W)).astype(np.float32)
+    o.filtered_gelu(x[:1], k, k)                      # warm-up (thread pool, page faults)
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max_reps and (time.perf_counter() - t_all < min_seconds or len(times) < 3):
+        t = time.perf_counter(); o.filtered_gelu(x, k, k); times.append(time.perf_counter() - t)
+    nbytes = 2 * x.size * 4
+    return {"value": nbytes / float(np.median(times)) / 1e9, "unit": UNIT, "cores": o.num_threads(),
+            "kind": "port", "reps": len(times),
+            "sample": f"filtered_gelu fwd fp32 on [{sample_b},{C},{H},{W}] (1/{WORKLOAD['B'] // sample_b} of the GPU batch), "
+                      f"median of {len(times)} runs, OpenMP over planes, host has {os.cpu_count()} logical cpus"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as o
+    o.build()
+    k = o.lowpass_taps(np.pi / 2, 3, 2.0)
+    C, H, W = WORKLOAD["C"], WORKLOAD["H"], WORKLOAD["W"]
+    sb = 32
+    x = np.random.default_rng(0).standard_normal((sb, C, H, W)).astype(np.float32)
+    for _ in range(args.warmup):
+        o.filtered_gelu(x, k, k)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        o.filtered_gelu(x, k, k)
+    dt = time.perf_counter() - t
+    val = args.steps * 2 * x.size * 4 / dt / 1e9
+    sample = f"each step = filtered_gelu fwd fp32 on [{sb},{C},{H},{W}] (1/{WORKLOAD['B'] // sb} of the GPU batch)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "filtered_gelu_fwd fp32 [256,128,64,64] N=3 beta=2 omega=pi/2", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": o.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---- sweep over the other ops / shapes / dtypes (reported, not the headline) ------------------
+def sweep(afr, quick):
+    k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
+    k6 = afr.circularLowpassKernel(np.pi / 2, 6, 2)
+    shapes = [(256, 128, 64, 64), (1024, 64, 32, 32), (16, 64, 256, 256), (128, 512, 32, 32),
+              (4096, 256, 4, 4), (4096, 128, 8, 8), (4096, 64, 16, 16), (2048, 32, 32, 32)]
+    if quick:
+        shapes = shapes[:2] + shapes[4:5]
+    rows = []
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")   # 256 MiB > L2
+
+    def tm(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    for shape in shapes:
+        for dt, es in ((torch.float32, 4), (torch.bfloat16, 2)):
+            x = torch.randn(shape, device="cuda").to(dt)
+            n = x.numel()
+            dy = torch.randn_like(x)
+            ops = {
+                "filtered_gelu_fwd": (lambda: afr.ops._fgelu_fwd(x, None, afr.Taps(k), afr.Taps(k)), 2 * n * es),
+                "filtered_gelu_bwd": (lambda: afr.ops._fgelu_bwd(x, None, dy, afr.Taps(k), afr.Taps(k)), 3 * n * es),
+                "up2x_fwd": (lambda: afr.ops._up_fwd(x, afr.Taps(k), dt), 5 * n * es),
+                "down2x_fwd": (lambda: afr.ops._down_fwd(x, afr.Taps(k)), 1.25 * n * es),
+            }
+            if shape == shapes[0]:
+                ops["filtered_gelu_fwd_N6_generic"] = (lambda: afr.ops._fgelu_fwd(x, None, afr.Taps(k6), afr.Taps(k6)), 2 * n * es)
+                for path in ("direct",):
+                    def f(path=path):
+                        afr.set_path(path)
+                        try:
+                            afr.ops._fgelu_fwd(x, None, afr.Taps(k), afr.Taps(k))
+                        finally:
+                            afr.set_path("auto")
+                    ops["filtered_gelu_fwd_" + path] = (f, 2 * n * es)
+            for name, (fn, nbytes) in ops.items():
+                ms = tm(fn)
+                rows.append({"op": name, "shape": list(shape), "dtype": "f32" if es == 4 else "bf16",
+                             "ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1), "kernel": afr.last_kernel()})
+            del x, dy
+    return rows
+
+
+# ---- DDPM Config-D reverse steps (BASELINE configs[2]) ---------------------------------------------
+def ddpm_v3(afr, ws, rank, global_batch, steps, warmup):
+    from aliasfree_b200 import parallel
+    torch.manual_seed(0)
+    net = afr.UNet(c_in=3, c_out=3, image_size=32, f_settings=FS, variant=3).cuda().eval()
+    diff = afr.Diffusion(noise_steps=1000, img_size=32, device="cuda")
+    lo, hi = parallel.shard_bounds(global_batch, rank, ws)
+    n = hi - lo
+    x = torch.randn(n, 3, 32, 32, device="cuda")
+    state = {"i": 999}
+
+    def step():
+        with torch.no_grad():
+            diff._reverse_step(net, x, state["i"], torch.randn_like(x))
+        state["i"] -= 1
+
+    l0 = afr.launch_count()
+    total_ms, _ = timed_loop(step, steps, warmup, ws)
+    launches = (afr.launch_count() - l0) // (steps + warmup)
+    ms = total_ms / steps
+    return {"samples_per_sec": global_batch / (999 * ms / 1e3), "ms_per_reverse_step": ms,
+            "global_batch": global_batch, "per_rank_batch": n, "steps_timed": steps,
+            "note": "random-init UNet variant=3 c=3 32x32, fp32 (PyTorch default TF32 conv); "
+                    "samples/sec = batch / (999 x measured ms per reverse step); strong scaling over ranks",
+            "afr_launches_per_step": int(launches)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--full-sweep", action="store_true")
+    ap.add_argument("--no-ddpm", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ddpm-batch", type=int, default=4096)
+    ap.add_argument("--path", default="auto", choices=["auto", "direct", "tma", "generic"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    rank, ws, local = dist_setup(args.gpus)
+    import aliasfree_b200 as afr
+    afr.set_path(args.path)
+    B, C, H, W = (WORKLOAD[k] for k in "BCHW")
+    torch.manual_seed(rank)
+    x = torch.randn(B, C, H, W, device="cuda")
+    y = torch.empty_like(x)
+    k = afr.Taps(afr.circularLowpassKernel(np.pi / 2, 3, 2))
+    nbytes = 2 * x.numel() * 4                       # read x + write y
+    L = afr._native.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        rc = L.afr_filtered_gelu_fwd(x.data_ptr(), None, y.data_ptr(), B, C, H, W, k.ptr, k.n, k.ptr, k.n, 0, stream)
+        assert rc == 0, L.afr_last_error()
+
+    clocks = ClockSampler(local)
+    l0 = afr.launch_count()
+    for _ in range(args.warmup):
+        step()
+    clocks.start()
+    total_ms, per = timed_loop(step, args.steps, 0, ws, per_step_events=True)
+    clk = clocks.stop()
+    launches = afr.launch_count() - l0 - args.warmup
+    kernel = afr.last_kernel()
+    ms_step = total_ms / args.steps
+    value = ws * nbytes / ms_step / 1e6
+    peak, peak_src = measured_peaks()
+    k_ms = float(np.mean(per))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(kernel)
+        except Exception:
+            traffic = None
+    roof = {"bound": "hbm", "kernel": kernel, "achieved": nbytes / k_ms / 1e6, "peak": peak, "unit": "GB/s",
+            "frac": nbytes / k_ms / 1e6 / peak, "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": k_ms}
+
+    # end to end through the C ABI with HOST buffers: H2D of x, kernel, D2H of y, every step
+    hx = torch.randn(B, C, H, W).pin_memory()
+    hy = torch.empty(B, C, H, W).pin_memory()
+
+    def e2e_step():
+        x.copy_(hx, non_blocking=True)
+        step()
+        hy.copy_(y, non_blocking=True)
+
+    e_steps = max(3, min(args.steps, 10))
+    e_total, _ = timed_loop(e2e_step, e_steps, 3, ws)
+    e2e = {"value": ws * nbytes / (e_total / e_steps) / 1e6, "unit": UNIT, "h2d_bytes_per_step": x.numel() * 4,
+           "d2h_bytes_per_step": y.numel() * 4, "ms_per_step": e_total / e_steps,
+           "api": "afr_filtered_gelu_fwd (C ABI) fed from / drained to pinned host buffers"}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": f"filtered_gelu_fwd fp32 [{B},{C},{H},{W}] per GPU, N=3 beta=2 omega=pi/2 "
+                                  f"(BASELINE configs[4] microbench tensor)",
+                      "l2": "input and output are 512 MiB each (> 126 MB L2); no flush needed", "path": args.path,
+                      "parallelism": f"batch-sharded x{ws}, no collective"},
+           "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+
+    if rank == 0 and ws == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_reference(sample_b=32)
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    if not args.no_sweep and ws == 1:
+        torch.cuda.empty_cache()
+        out["sweep"] = sweep(afr, quick=not args.full_sweep)
+    if not args.no_ddpm:
+        torch.cuda.empty_cache()
+        out["ddpm_v3"] = ddpm_v3(afr, ws, rank, args.ddpm_batch, steps=min(args.steps, 5), warmup=3)
+    if rank == 0:
+        print(json.dumps(out))
+    if ws > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,118 @@
+/*
+ * afr.h -- C ABI of libafr_b200.so: the alias-free resampling hot path of
+ * MDFahimAnjum/AliasFree-Diffusion-Models-PyTorch as hand-written CUDA for sm_100a.
+ *
+ * The reference has no FFI: its boundary is two Python free functions and the block
+ * classes that call them.  Each entry point below names the
+ * reference code it replaces; INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - all tensors are dense NCHW device buffers owned by the caller; the library
+ *     never allocates, frees or keeps device memory;
+ *   - `taps*` are HOST pointers to N*N float32 row-major filter taps (the tensor
+ *     returned by circularLowpassKernel, modules/filtrs.py:20-37); they are copied
+ *     into the kernel's parameter space at launch, never uploaded separately;
+ *   - `dtype`: AFR_F32 or AFR_BF16 storage; arithmetic is always fp32;
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream); calls only enqueue
+ *     work, never synchronise, and are deterministic (no atomics);
+ *   - return value: AFR_OK or an afr_status; afr_last_error() gives a thread-local
+ *     human-readable message.  There is no CPU fallback.
+ */
+#ifndef AFR_H_
+#define AFR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFR_VERSION 100      /* 0.1.0 */
+#define AFR_MAX_TAPS 16      /* largest supported N (filter is N x N) */
+
+typedef enum { AFR_F32 = 0, AFR_BF16 = 1 } afr_dtype;
+
+typedef enum {
+    AFR_OK = 0,
+    AFR_ERR_BAD_SHAPE = 1,     /* non-positive dims, planes overflow */
+    AFR_ERR_BAD_TAPS = 2,      /* N < 1, N > AFR_MAX_TAPS or NULL taps */
+    AFR_ERR_BAD_DTYPE = 3,
+    AFR_ERR_NULL_POINTER = 4,
+    AFR_ERR_MISALIGNED = 5,    /* buffer not aligned to its element size */
+    AFR_ERR_CUDA = 6,          /* launch / driver error, see afr_last_error() */
+    AFR_ERR_UNSUPPORTED = 7    /* e.g. resampling factor != 2 */
+} afr_status;
+
+/* Path selection for the N==3 kernels (testing / benchmarking aid). */
+typedef enum {
+    AFR_PATH_AUTO = 0,      /* TMA-staged tiles when the shape allows, else direct */
+    AFR_PATH_DIRECT = 1,    /* register-strip kernel reading global memory directly */
+    AFR_PATH_TMA = 2,       /* force the TMA tile kernel (error if shape unsupported) */
+    AFR_PATH_GENERIC = 3    /* force the runtime-N shared-memory kernels */
+} afr_path;
+
+int afr_version(void);
+const char *afr_last_error(void);
+const char *afr_status_string(int status);
+/* Sets the kernel path for subsequent calls of this process; returns the old one. */
+int afr_set_path(int path);
+/* Name of the kernel the last call on this thread launched (for tests/profiles). */
+const char *afr_last_kernel(void);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+uint64_t afr_launch_count(void);
+
+/* custom_upsample(x, sinc_filter, factor=2)            modules/filtrs.py:79-94
+ * x [B,C,H,W] (in_dtype) -> u [B,C,2H,2W] (out_dtype).  Zero-stuff x2 then depthwise
+ * N x N cross-correlation with 'same' zero padding; no gain compensation.  The
+ * reference always returns fp32 (filtrs.py:85); out_dtype lets bf16 pipelines keep bf16. */
+int afr_up2x_fwd(const void *x, void *u, int B, int C, int H, int W,
+                 const float *taps, int N, int in_dtype, int out_dtype, void *stream);
+
+/* autograd adjoint of custom_upsample: du [B,C,2H,2W] -> dx [B,C,H,W] (H, W = input dims) */
+int afr_up2x_bwd(const void *du, void *dx, int B, int C, int H, int W,
+                 const float *taps, int N, int du_dtype, int dx_dtype, void *stream);
+
+/* custom_downsample(x, jinc_filter, factor=2)          modules/filtrs.py:71-77
+ * v [B,C,H,W] -> y [B,C,ceil(H/2),ceil(W/2)], contiguous (the reference returns a
+ * strided view of the full-resolution convolution; values are identical). */
+int afr_down2x_fwd(const void *v, void *y, int B, int C, int H, int W,
+                   const float *taps, int N, int dtype, void *stream);
+
+/* adjoint of custom_downsample: dy [B,C,ceil(H/2),ceil(W/2)] -> dv [B,C,H,W] */
+int afr_down2x_bwd(const void *dy, void *dv, int B, int C, int H, int W,
+                   const float *taps, int N, int dtype, void *stream);
+
+/* Filtered nonlinearity  custom_downsample(gelu(custom_upsample(x + residual, up)), down)
+ * modules/ddpm_utils.py:123-125, 129-131 (with `x = x + residual` of :128 fused when
+ * residual != NULL), 137-139.  GELU is the exact erf form.  x, residual, y: [B,C,H,W]. */
+int afr_filtered_gelu_fwd(const void *x, const void *residual, void *y,
+                          int B, int C, int H, int W,
+                          const float *taps_up, int N_up, const float *taps_down, int N_down,
+                          int dtype, void *stream);
+
+/* adjoint of the above wrt (x + residual): recomputes u from x, reads dy, writes dx
+ * (d/dx and d/dresidual are the same tensor).  No saved 4x intermediates. */
+int afr_filtered_gelu_bwd(const void *x, const void *residual, const void *dy, void *dx,
+                          int B, int C, int H, int W,
+                          const float *taps_up, int N_up, const float *taps_down, int N_down,
+                          int dtype, void *stream);
+
+/* Diffusion.rotate_2d_matrix(matrix, degrees)          modules/ddpm_models.py:421-429
+ * = scipy.ndimage.rotate(axes=(2,3), reshape=False, order=3, mode='grid-wrap'):
+ * periodic cubic B-spline prefilter + 4x4-tap gather, entirely on device.
+ * x, y: [B,C,H,W] fp32 (dtype must be AFR_F32), H*W <= 16384. x may equal y only if
+ * they do not alias partially (in-place is NOT supported). */
+int afr_rotate_periodic_cubic(const void *x, void *y, int B, int C, int H, int W,
+                              double degrees, int dtype, void *stream);
+
+/* Fused posterior update of Algorithm 1 (modules/ddpm_models.py:374):
+ * x <- ca * (x - cb * eps) + cc * noise, elementwise over n floats (fp32). noise may be NULL. */
+int afr_ddpm_update(void *x, const void *eps, const void *noise, int64_t n,
+                    float ca, float cb, float cc, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFR_H_ */

@@ -1,0 +1,258 @@
+"""GPU parity tests: CUDA kernels (through the C ABI) vs the reference's own outputs
+(tests/golden) and vs the CPU oracle on seeded inputs.  Tolerances are the north star's:
+fp32  max|y - y_ref| / max|y_ref| <= 1e-5;  bf16 <= 2^-8 against the fp32 oracle evaluated
+on the bf16-rounded input."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, relmax
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 2.0 ** -8
+
+
+@pytest.fixture(scope="module")
+def afr():
+    import aliasfree_b200 as m
+    assert torch.cuda.is_available()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return m
+
+
+def dev(a, dtype=torch.float32, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda().to(dtype)
+    return t.requires_grad_(True) if grad else t
+
+
+def host(t):
+    return t.detach().float().cpu().numpy()
+
+
+def _names():
+    return [str(s) for s in golden("resample.npz")["names"]]
+
+
+def _paths_for(afr, name, g):
+    n = g[f"{name}.ku"].shape[0]
+    H, W = g[f"{name}.x"].shape[-2:]
+    paths = ["auto", "generic"]
+    if n == 3 and g[f"{name}.kd"].shape[0] == 3 and W % 4 == 0:
+        paths.append("direct")
+        if H >= 16 and W >= 16:
+            paths.append("tma")
+    return paths
+
+
+@pytest.mark.parametrize("name", _names())
+def test_golden_resample_all_paths(afr, name):
+    g = golden("resample.npz")
+    ku, kd = g[f"{name}.ku"], g[f"{name}.kd"]
+    for path in _paths_for(afr, name, g):
+        afr.set_path(path)
+        try:
+            x = dev(g[f"{name}.x"], grad=True)
+            u = afr.custom_upsample(x, torch.from_numpy(ku))
+            assert u.dtype == torch.float32 and u.is_contiguous()
+            assert relmax(host(u), g[f"{name}.up"]) <= FP32_TOL, path
+            (dx,) = torch.autograd.grad(u, x, dev(g[f"{name}.du"]))
+            assert relmax(host(dx), g[f"{name}.dx_up"]) <= FP32_TOL, path
+
+            d = afr.custom_downsample(x, torch.from_numpy(kd))
+            assert relmax(host(d), g[f"{name}.down"]) <= FP32_TOL, path
+            (dx,) = torch.autograd.grad(d, x, dev(g[f"{name}.dd"]))
+            assert relmax(host(dx), g[f"{name}.dx_down"]) <= FP32_TOL, path
+
+            y = afr.filtered_gelu(x, ku, kd)
+            assert relmax(host(y), g[f"{name}.fused"]) <= FP32_TOL, path
+            (dx,) = torch.autograd.grad(y, x, dev(g[f"{name}.dy"]))
+            assert relmax(host(dx), g[f"{name}.dx_fused"]) <= FP32_TOL, path
+        finally:
+            afr.set_path("auto")
+
+
+ORACLE_SHAPES = [  # (B, C, H, W, N_up, N_dn)
+    (2, 4, 32, 32, 3, 3), (1, 3, 64, 64, 3, 3), (1, 2, 128, 128, 3, 3), (1, 1, 256, 256, 3, 3),
+    (2, 3, 16, 16, 3, 3), (3, 5, 48, 24, 3, 3), (1, 2, 40, 200, 3, 3), (37, 3, 4, 4, 3, 3),
+    (5, 7, 8, 8, 3, 3), (1, 2, 20, 12, 3, 3), (1, 1, 33, 31, 3, 3), (2, 2, 16, 16, 6, 6),
+    (1, 2, 24, 24, 3, 6), (1, 1, 17, 19, 5, 4), (1, 1, 12, 12, 16, 16), (1, 300, 16, 16, 3, 3),
+]
+
+
+@pytest.mark.parametrize("shape", ORACLE_SHAPES)
+def test_oracle_fp32(afr, oracle, shape):
+    B, C, H, W, nu, nd = shape
+    rng = np.random.default_rng(hash(shape) % (2 ** 31))
+    ku = oracle.lowpass_taps(np.pi / 2, nu, 2.0)
+    kd = oracle.lowpass_taps(0.7 * np.pi, nd, 1.0)
+    ku = (ku + 0.02 * rng.standard_normal(ku.shape)).astype(np.float32)   # break the symmetry:
+    kd = (kd + 0.02 * rng.standard_normal(kd.shape)).astype(np.float32)   # catches flipped taps
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    r = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    dy = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    du = rng.standard_normal((B, C, 2 * H, 2 * W)).astype(np.float32)
+    dd = rng.standard_normal((B, C, (H + 1) // 2, (W + 1) // 2)).astype(np.float32)
+    paths = ["auto", "generic"]
+    if nu == 3 and nd == 3 and W % 4 == 0:
+        paths.append("direct")
+        if H >= 16 and W >= 16:
+            paths.append("tma")
+    want = dict(up=oracle.up2x(x, ku), up_b=oracle.up2x_bwd(du, ku), dn=oracle.down2x(x, kd),
+                dn_b=oracle.down2x_bwd(dd, kd, H, W), f=oracle.filtered_gelu(x, ku, kd),
+                f_b=oracle.filtered_gelu_bwd(x, dy, ku, kd), fr=oracle.filtered_gelu(x + r, ku, kd),
+                fr_b=oracle.filtered_gelu_bwd(x + r, dy, ku, kd))
+    for path in paths:
+        afr.set_path(path)
+        try:
+            xt, rt = dev(x, grad=True), dev(r, grad=True)
+            u = afr.up2x(xt, ku)
+            assert relmax(host(u), want["up"]) <= FP32_TOL, path
+            assert relmax(host(torch.autograd.grad(u, xt, dev(du))[0]), want["up_b"]) <= FP32_TOL, path
+            d = afr.down2x(xt, kd)
+            assert relmax(host(d), want["dn"]) <= FP32_TOL, path
+            assert relmax(host(torch.autograd.grad(d, xt, dev(dd))[0]), want["dn_b"]) <= FP32_TOL, path
+            y = afr.filtered_gelu(xt, ku, kd)
+            assert relmax(host(y), want["f"]) <= FP32_TOL, path
+            assert relmax(host(torch.autograd.grad(y, xt, dev(dy))[0]), want["f_b"]) <= FP32_TOL, path
+            y = afr.filtered_gelu(xt, ku, kd, residual=rt)
+            assert relmax(host(y), want["fr"]) <= FP32_TOL, path
+            gx, gr = torch.autograd.grad(y, (xt, rt), dev(dy))
+            assert relmax(host(gx), want["fr_b"]) <= FP32_TOL, path
+            assert torch.equal(gx, gr)
+        finally:
+            afr.set_path("auto")
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 32, 32), (1, 2, 64, 64), (9, 3, 4, 4), (2, 2, 16, 24), (1, 2, 9, 7)])
+@pytest.mark.parametrize("n", [3, 6])
+def test_oracle_bf16(afr, oracle, shape, n):
+    rng = np.random.default_rng(7)
+    ku = oracle.lowpass_taps(np.pi / 2, n, 2.0); kd = oracle.lowpass_taps(np.pi / 2, n, 2.0)
+    xb = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
+    dyb = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
+    x32, dy32 = host(xb), host(dyb)
+    for path in (["auto", "generic", "direct"] if (n == 3 and shape[-1] % 4 == 0) else ["auto"]):
+        afr.set_path(path)
+        try:
+            xt = xb.clone().requires_grad_(True)
+            y = afr.filtered_gelu(xt, ku, kd)
+            assert y.dtype == torch.bfloat16
+            assert relmax(host(y), oracle.filtered_gelu(x32, ku, kd)) <= BF16_TOL, path
+            (dx,) = torch.autograd.grad(y, xt, dyb)
+            assert relmax(host(dx), oracle.filtered_gelu_bwd(x32, dy32, ku, kd)) <= BF16_TOL, path
+            u = afr.up2x(xt, ku)
+            assert u.dtype == torch.bfloat16
+            assert relmax(host(u), oracle.up2x(x32, ku)) <= BF16_TOL, path
+            assert afr.custom_upsample(xt, ku).dtype == torch.float32      # reference: always fp32
+            assert relmax(host(afr.custom_upsample(xt, ku)), oracle.up2x(x32, ku)) <= FP32_TOL, path
+            d = afr.down2x(xt, kd)
+            assert relmax(host(d), oracle.down2x(x32, kd)) <= BF16_TOL, path
+        finally:
+            afr.set_path("auto")
+
+
+def test_full_size_properties(afr, oracle):
+    """BASELINE-size tensors (too big for the oracle): linearity, adjointness, cross-path equality,
+    and oracle spot checks on a few planes."""
+    torch.manual_seed(0)
+    k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
+    x = torch.randn(64, 64, 64, 64, device="cuda")
+    z = torch.randn_like(x)
+    # linearity of the resamplers
+    assert relmax(host(afr.up2x(x + z, k)[:2]), host((afr.up2x(x, k) + afr.up2x(z, k))[:2])) <= 2e-6
+    assert relmax(host(afr.down2x(x + z, k)[:2]), host((afr.down2x(x, k) + afr.down2x(z, k))[:2])) <= 2e-6
+    # <down(x), d> == <x, down^T(d)> ; <up(x), d> == <x, up^T(d)>
+    xg = x.clone().requires_grad_(True)
+    d = afr.down2x(xg, k); dd = torch.randn_like(d)
+    (gx,) = torch.autograd.grad(d, xg, dd)
+    lhs, rhs = (d.double() * dd.double()).sum().item(), (x.double() * gx.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    u = afr.up2x(xg, k); du = torch.randn_like(u)
+    (gx,) = torch.autograd.grad(u, xg, du)
+    lhs, rhs = (u.double() * du.double()).sum().item(), (x.double() * gx.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    # fused: all kernel families agree, and match the oracle on sampled planes
+    outs = {}
+    dy = torch.randn_like(x)
+    for path in ("tma", "direct", "generic"):
+        afr.set_path(path)
+        try:
+            xg = x.clone().requires_grad_(True)
+            y = afr.filtered_gelu(xg, k, k)
+            outs[path] = (y.detach(), torch.autograd.grad(y, xg, dy)[0])
+        finally:
+            afr.set_path("auto")
+    for path in ("direct", "generic"):
+        assert (outs[path][0] - outs["tma"][0]).abs().max().item() <= 2e-6
+        assert (outs[path][1] - outs["tma"][1]).abs().max().item() <= 2e-6
+    kn = k.numpy()
+    for b, c in [(0, 0), (17, 5), (63, 63)]:
+        xs, dys = host(x[b, c]), host(dy[b, c])
+        assert relmax(host(outs["tma"][0][b, c]), oracle.filtered_gelu(xs, kn, kn)) <= FP32_TOL
+        assert relmax(host(outs["tma"][1][b, c]), oracle.filtered_gelu_bwd(xs, dys, kn, kn)) <= FP32_TOL
+
+
+def test_kernel_selection(afr):
+    k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
+    afr.filtered_gelu(torch.randn(2, 2, 32, 32, device="cuda"), k, k)
+    assert afr.last_kernel() == "fgelu3_tma_kernel"
+    afr.filtered_gelu(torch.randn(2, 2, 4, 4, device="cuda"), k, k)
+    assert afr.last_kernel() == "fgelu3_direct_kernel"
+    k6 = afr.circularLowpassKernel(np.pi / 2, 6, 2)
+    afr.filtered_gelu(torch.randn(2, 2, 8, 8, device="cuda"), k6, k6)
+    assert afr.last_kernel() == "fgelu_generic_kernel"
+    n0 = afr.launch_count()
+    afr.up2x(torch.randn(1, 1, 8, 8, device="cuda"), k)
+    assert afr.launch_count() == n0 + 1
+
+
+def test_noncontiguous_and_channels_last(afr, oracle):
+    k = oracle.lowpass_taps(np.pi / 2, 3, 2.0)
+    x = torch.randn(2, 6, 16, 16, device="cuda")
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    y = afr.filtered_gelu(xcl, k, k)
+    assert y.is_contiguous()
+    assert relmax(host(y), oracle.filtered_gelu(host(x), k, k)) <= FP32_TOL
+    xs = x[:, ::2]
+    assert relmax(host(afr.down2x(xs, k)), oracle.down2x(host(xs), k)) <= FP32_TOL
+
+
+def test_errors(afr):
+    k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
+    x = torch.randn(1, 1, 8, 8, device="cuda")
+    with pytest.raises(RuntimeError):
+        afr.up2x(torch.randn(1, 1, 8, 8), k)                       # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        afr.custom_upsample(x, k, factor=4)
+    with pytest.raises(RuntimeError):
+        afr.up2x(x, torch.ones(17, 17) / 289.0)                    # N > AFR_MAX_TAPS
+    with pytest.raises(ValueError):
+        afr.up2x(x, torch.ones(3, 4))
+    with pytest.raises(TypeError):
+        afr.up2x(x.half(), k)
+    assert afr.up2x(torch.empty(0, 3, 8, 8, device="cuda"), k).shape == (0, 3, 16, 16)
+    assert torch.isnan(afr.filtered_gelu(torch.full((1, 1, 4, 4), float("nan"), device="cuda"), k, k)).all()
+
+
+def test_rotate(afr, oracle):
+    g = golden("rotate.npz")
+    x = dev(g["x"])
+    for i, a in enumerate(g["angles"]):
+        assert np.abs(host(afr.rotate(x, float(a))) - g[f"y{i}"]).max() <= 1e-5, a
+    assert np.abs(host(afr.rotate(dev(g["xr"]), 7.5)) - g["yr"]).max() <= 1e-5
+    big = torch.randn(3, 2, 64, 48, device="cuda")
+    assert np.abs(host(afr.rotate(big, -33.3)) - oracle.rotate(host(big), -33.3)).max() <= 1e-5
+
+
+def test_ddpm_update(afr):
+    torch.manual_seed(1)
+    for n in (4096, 1001):
+        x, e, z = (torch.randn(n, device="cuda") for _ in range(3))
+        want = 1.01 * (x - 0.3 * e) + 0.2 * z
+        got = afr.ddpm_update_(x.clone(), e, z, 1.01, 0.3, 0.2)
+        assert (got - want).abs().max().item() <= 1e-6
+        got = afr.ddpm_update_(x.clone(), e, None, 1.01, 0.3, 0.0)
+        assert (got - 1.01 * (x - 0.3 * e)).abs().max().item() <= 1e-6

@@ -1,0 +1,203 @@
+"""CPU-only tests: host logic, filter design, module/state_dict compatibility, the C-ABI
+library's exported symbols, multi-rank plumbing on gloo.  No compute calls into the CUDA
+library here (there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+
+FS = dict(kernel_size=3, kaiser_beta=2, omega_c_down=np.pi / 2, omega_c_up=np.pi / 2)
+
+
+@pytest.fixture(scope="module")
+def afr():
+    import aliasfree_b200 as m
+    return m
+
+
+def test_filter_design_matches_reference(afr):
+    g = golden("taps.npz")
+    n = len([k for k in g.files if k.startswith("k")])
+    for i in range(n):
+        w, N, beta, has = g[f"p{i}"]
+        k = afr.circularLowpassKernel(w, int(N), beta if has else None)
+        assert k.dtype == torch.float32 and not k.requires_grad and k.device.type == "cpu"
+        np.testing.assert_allclose(k.numpy(), g[f"k{i}"], rtol=1e-6, atol=1e-9)
+
+
+def test_library_loads_and_exports_every_declared_symbol(afr):
+    header = open(os.path.join(ROOT, "include", "afr.h")).read()
+    declared = set(re.findall(r"\b(afr_[a-z0-9_]+)\s*\(", header))
+    declared -= {"afr_status", "afr_dtype", "afr_path"}
+    assert {"afr_up2x_fwd", "afr_filtered_gelu_bwd", "afr_rotate_periodic_cubic"} <= declared
+    path = afr.build()
+    L = ctypes.CDLL(path)
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert set(afr._native.EXPORTS) == declared
+    assert afr._native.lib().afr_version() == 100
+
+
+def test_c_abi_argument_errors_without_gpu(afr):
+    """Argument validation happens before any CUDA call, so it is testable on CPU."""
+    L = afr._native.lib()
+    taps = (ctypes.c_float * 9)(*([1 / 9.0] * 9))
+    assert L.afr_up2x_fwd(None, None, 1, 1, 0, 4, taps, 3, 0, 0, None) == 1      # bad shape
+    assert L.afr_up2x_fwd(None, None, 1, 1, 4, 4, taps, 17, 0, 0, None) == 2     # bad taps
+    assert L.afr_up2x_fwd(None, None, 1, 1, 4, 4, None, 3, 0, 0, None) == 2
+    assert L.afr_up2x_fwd(None, None, 1, 1, 4, 4, taps, 3, 5, 0, None) == 3      # bad dtype
+    assert L.afr_up2x_fwd(None, None, 1, 1, 4, 4, taps, 3, 0, 0, None) == 4      # null pointer
+    assert L.afr_up2x_fwd(None, None, 0, 1, 4, 4, taps, 3, 0, 0, None) == 0      # empty batch: no-op
+    assert L.afr_down2x_fwd(ctypes.c_void_p(2), ctypes.c_void_p(4), 1, 1, 4, 4, taps, 3, 0, None) == 5
+    assert b"misaligned" in L.afr_last_error()
+    assert L.afr_status_string(6) == b"CUDA error"
+
+
+def test_no_cpu_fallback(afr):
+    k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
+    x = torch.randn(1, 2, 8, 8)
+    for fn in (lambda: afr.up2x(x, k), lambda: afr.down2x(x, k), lambda: afr.filtered_gelu(x, k, k),
+               lambda: afr.rotate(x, 3.0), lambda: afr.custom_upsample(x, k)):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            fn()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "aliasfree-diffusion-models-pytorch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), f
+
+
+def test_state_dict_keys_match_reference_layout(afr):
+    net = afr.UNet(c_in=3, c_out=3, image_size=16, f_settings=FS, variant=3)
+    keys = set(net.state_dict())
+    for k in ("inc.conv1.weight", "inc.norm1.weight", "inc.norm1.bias", "down1.conv.0.conv1.weight",
+              "down1.emb_layer.1.weight", "down1.emb_layer.1.bias", "up1.conv.1.norm2.weight",
+              "sa1.mha.in_proj_weight", "sa3.ff_self.3.bias", "outc.weight", "outc.bias"):
+        assert k in keys, k
+    assert not any("filter" in k or "taps" in k for k in keys)
+    k2 = set(afr.UNet(c_in=3, c_out=3, image_size=16, f_settings=FS, variant=2).state_dict())
+    assert "down1.maxpool_conv.1.conv1.weight" in k2 and "up1.conv.0.norm1.weight" in k2
+    k1 = set(afr.UNet(c_in=3, c_out=3, image_size=16, f_settings=FS, variant=1).state_dict())
+    assert "down1.conv.0.double_conv.0.weight" in k1 and "inc.double_conv.1.weight" in k1
+    with pytest.raises(ValueError):
+        afr.UNet(variant=3)                     # f_settings missing, like the reference
+    with pytest.raises(ValueError):
+        afr.UNet(variant=7)
+
+
+def test_state_dict_is_strictly_loadable_from_reference():
+    if not os.path.isdir("/root/reference/modules"):
+        pytest.skip("no reference checkout on this machine")
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "imageio"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.path.insert(0, "/root/reference")
+    import modules.ddpm_models as rm
+    import aliasfree_b200 as afr
+    for v in (0, 1, 2, 3):
+        ref = rm.UNet(c_in=3, c_out=3, image_size=16, device="cpu", f_settings=FS, variant=v)
+        ours = afr.UNet(c_in=3, c_out=3, image_size=16, f_settings=FS, variant=v)
+        ours.load_state_dict(ref.state_dict(), strict=True)
+        assert [tuple(p.shape) for p in ours.parameters()] == [tuple(p.shape) for p in ref.parameters()]
+
+
+def test_variant0_unet_runs_on_cpu_and_matches_reference():
+    """Variant 0 has no filters, so the wiring itself can be checked on CPU against the reference."""
+    if not os.path.isdir("/root/reference/modules"):
+        pytest.skip("no reference checkout on this machine")
+    sys.path.insert(0, "/root/reference")
+    import modules.ddpm_models as rm
+    import aliasfree_b200 as afr
+    from _fill import fill_params_
+    ref = fill_params_(rm.UNet(c_in=3, c_out=3, image_size=16, device="cpu", variant=0))
+    ours = fill_params_(afr.UNet(c_in=3, c_out=3, image_size=16, variant=0))
+    x = torch.randn(2, 3, 16, 16); t = torch.tensor([3, 700])
+    with torch.no_grad():
+        assert torch.allclose(ours(x, t), ref(x, t), atol=1e-5, rtol=1e-5)
+
+
+def test_diffusion_schedule_and_tables(afr):
+    d = afr.Diffusion(noise_steps=50, img_size=8, device="cpu")
+    assert d.beta.shape == (50,) and abs(d.beta[0].item() - 1e-4) < 1e-9 and abs(d.beta[-1].item() - 0.02) < 1e-9
+    assert torch.allclose(d.alpha_hat, torch.cumprod(1 - d.beta, 0))
+    i = 17
+    assert abs(d._ca[i] - (1 / torch.sqrt(d.alpha[i])).item()) < 1e-7
+    assert abs(d._cb[i] - ((1 - d.alpha[i]) / torch.sqrt(1 - d.alpha_hat[i])).item()) < 1e-7
+    t = d.sample_timesteps(1000)
+    assert t.min() >= 1 and t.max() < 50
+    x = torch.randn(4, 1, 8, 8)
+    xt, eps = d.noise_images(x, torch.tensor([1, 5, 20, 49]))
+    assert xt.shape == x.shape and eps.shape == x.shape
+
+
+def test_shard_bounds(afr):
+    from aliasfree_b200.parallel import shard_bounds
+    for n, ws in [(4096, 8), (10, 4), (3, 8), (0, 2)]:
+        spans = [shard_bounds(n, r, ws) for r in range(ws)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["AFR_ROOT"])
+import aliasfree_b200 as afr
+from aliasfree_b200 import parallel
+dist.init_process_group("gloo")
+rank, ws = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(100 + rank)                       # different init per rank on purpose
+net = afr.UNet(c_in=1, c_out=1, image_size=8, variant=0)     # variant 0: runs on CPU
+ddp = parallel.FlatGradAllReduce(net)               # broadcasts rank 0's parameters
+flat0 = torch.cat([p.detach().flatten() for p in net.parameters()])
+gathered = [torch.empty_like(flat0) for _ in range(ws)]
+dist.all_gather(gathered, flat0)
+assert all(torch.equal(gathered[0], g) for g in gathered), "broadcast failed"
+diff = afr.Diffusion(noise_steps=20, img_size=8, device="cpu")
+opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+torch.manual_seed(7)
+full = torch.rand(4 * ws, 1, 8, 8) * 2 - 1          # identical global batch on every rank
+lo, hi = parallel.shard_bounds(full.shape[0], rank, ws)
+# local gradient on the shard, then the single all-reduce
+t = torch.arange(1, 1 + full.shape[0]) % 19 + 1
+torch.manual_seed(11); eps = torch.randn_like(full)
+def loss_on(sl):
+    sa = torch.sqrt(diff.alpha_hat[t[sl]])[:, None, None, None]; sb = torch.sqrt(1 - diff.alpha_hat[t[sl]])[:, None, None, None]
+    return torch.nn.functional.mse_loss(net(sa * full[sl] + sb * eps[sl], t[sl]), eps[sl])
+ddp.zero_grad(); loss_on(slice(lo, hi)).backward(); ddp.sync()
+sharded = ddp.flat.clone()
+ddp.zero_grad(); loss_on(slice(0, full.shape[0])).backward()
+assert torch.allclose(sharded, ddp.flat, atol=1e-6, rtol=1e-4), (sharded - ddp.flat).abs().max()
+# sharded sampling: shards tile the global batch, no communication needed
+x, res = None, None
+lo2, hi2 = parallel.shard_bounds(6, rank, ws)
+assert hi2 - lo2 == 6 // ws
+dist.barrier()
+if rank == 0: print("GLOO_OK")
+'''
+
+
+def test_two_rank_gloo_data_parallel(tmp_path):
+    """world_size=2 on CPU: parameter broadcast and flat-gradient all-reduce reproduce the
+    global-batch gradient (equal shards, MSE mean)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, AFR_ROOT=ROOT, OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "GLOO_OK" in out.stdout
