@@ -23,6 +23,7 @@ using namespace afr;
 namespace {
 
 thread_local char g_err[512] = "";
+thread_local char g_detail[320] = "";
 thread_local const char *g_last_kernel = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_path{-1};
@@ -58,7 +59,15 @@ int cuda_status(cudaError_t e, const char *what)
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return AFR_OK;
     }
-    return fail(AFR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return fail(AFR_ERR_CUDA, "%s: %s%s%s", what, cudaGetErrorString(e), g_detail[0] ? " -- " : "", g_detail);
+}
+
+// The runtime is shared with PyTorch (one libcudart.so.12): drop any stale non-sticky error a
+// previous, unrelated runtime call left behind so that it is not attributed to our launch.
+void begin_call()
+{
+    g_detail[0] = 0;
+    (void)cudaGetLastError();
 }
 
 bool dtype_ok(int d) { return d == AFR_F32 || d == AFR_BF16; }
@@ -89,6 +98,16 @@ void set_taps3(Taps3 &t, const float *k, bool flip)
 }
 
 }  // namespace
+
+namespace afr {
+void set_detail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_detail, sizeof(g_detail), fmt, ap);
+    va_end(ap);
+}
+}  // namespace afr
 
 extern "C" {
 
@@ -129,6 +148,7 @@ int afr_up2x_fwd(const void *x, void *u, int B, int C, int H, int W, const float
     if (!x || !u) return fail(AFR_ERR_NULL_POINTER, "x or u is NULL");
     if (!elem_aligned(x, in_dtype) || !elem_aligned(u, out_dtype)) return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
     cudaStream_t s = (cudaStream_t)stream;
+    begin_call();
     const int path = current_path();
     if (N == 3 && path != AFR_PATH_GENERIC && n3_up_supported(H, W, x, u, in_dtype, out_dtype)) {
         Taps3 k; set_taps3(k, taps, false);
@@ -151,6 +171,7 @@ int afr_up2x_bwd(const void *du, void *dx, int B, int C, int H, int W, const flo
     if (!du || !dx) return fail(AFR_ERR_NULL_POINTER, "du or dx is NULL");
     if (!elem_aligned(du, du_dtype) || !elem_aligned(dx, dx_dtype)) return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
     cudaStream_t s = (cudaStream_t)stream;
+    begin_call();
     const int path = current_path();
     if (du_dtype != dx_dtype)
         return fail(AFR_ERR_UNSUPPORTED, "up2x_bwd needs du and dx of one dtype (cast du on the host side)");
@@ -175,6 +196,7 @@ int afr_down2x_fwd(const void *v, void *y, int B, int C, int H, int W, const flo
     if (!v || !y) return fail(AFR_ERR_NULL_POINTER, "v or y is NULL");
     if (!elem_aligned(v, dtype) || !elem_aligned(y, dtype)) return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
     cudaStream_t s = (cudaStream_t)stream;
+    begin_call();
     const int path = current_path();
     if (N == 3 && path != AFR_PATH_GENERIC && n3_down_supported(H, W, v, y, dtype)) {
         Taps3 k; set_taps3(k, taps, false);
@@ -197,6 +219,7 @@ int afr_down2x_bwd(const void *dy, void *dv, int B, int C, int H, int W, const f
     if (!dy || !dv) return fail(AFR_ERR_NULL_POINTER, "dy or dv is NULL");
     if (!elem_aligned(dy, dtype) || !elem_aligned(dv, dtype)) return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
     cudaStream_t s = (cudaStream_t)stream;
+    begin_call();
     const int path = current_path();
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     if (N == 3 && path != AFR_PATH_GENERIC && (H % 2) == 0 && (W % 2) == 0 &&
@@ -225,6 +248,7 @@ static int fused_common(const void *x, const void *residual, const void *dy, voi
         (bwd && !elem_aligned(dy, dtype)))
         return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
     cudaStream_t s = (cudaStream_t)stream;
+    begin_call();
     const int path = current_path();
     const void *ptrs[4] = {x, residual, bwd ? dy : nullptr, out};
     if (N_up == 3 && N_down == 3 && path != AFR_PATH_GENERIC && n3_fgelu_supported(H, W, ptrs, 4, dtype)) {
@@ -278,6 +302,7 @@ int afr_rotate_periodic_cubic(const void *x, void *y, int B, int C, int H, int W
     if (!x || !y) return fail(AFR_ERR_NULL_POINTER, "x or y is NULL");
     if (x == y) return fail(AFR_ERR_UNSUPPORTED, "in-place rotate is not supported");
     if (!elem_aligned(x, dtype) || !elem_aligned(y, dtype)) return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
+    begin_call();
     g_last_kernel = "rotate_kernel";
     return cuda_status(rotate_periodic_cubic((const float *)x, (float *)y, planes, H, W, degrees,
                                              (cudaStream_t)stream),
@@ -290,6 +315,7 @@ int afr_ddpm_update(void *x, const void *eps, const void *noise, int64_t n, floa
     if (n < 0) return fail(AFR_ERR_BAD_SHAPE, "n < 0");
     if (n == 0) return AFR_OK;
     if (!x || !eps) return fail(AFR_ERR_NULL_POINTER, "x or eps is NULL");
+    begin_call();
     g_last_kernel = "ddpm_update_kernel";
     return cuda_status(ddpm_update((float *)x, (const float *)eps, (const float *)noise, (long)n, ca, cb,
                                    cc, (cudaStream_t)stream),

@@ -84,28 +84,36 @@ __device__ __forceinline__ float4 lds4(const bf16 *p)
 }
 
 // ---- exact-erf GELU in fp32 with one MUFU ------------------------------------------
-// gelu(x)  = relu(x) - t*E*R(t)
-// gelu'(x) = 0.5 + sign(x)*(0.5 - E*R(t)) + x*E/sqrt(2 pi)
-// with t = min(|x|, 5.5), E = exp(-t^2/2) and R(t) = Phi(-t) exp(t^2/2) (half the scaled
-// complementary error function), a slowly varying function fitted by a degree-9
-// polynomial (tools/fit_gelu.py).  Max abs error vs erf-GELU evaluated in double:
-// 6.9e-7 (value), 8.7e-7 (derivative); beyond the clamp the true tail is < 1.1e-7.
-// This replaces erff() (about 2x the instructions, two MUFU ops) -- the fused
-// filtered-GELU kernel is issue-bound, not HBM-bound, so the cost of GELU sets its speed.
-__device__ __forceinline__ float gelu_poly_R(float t)
+// The fused filtered-GELU kernels are issue-bound (4 GELUs per output element), so the cost
+// of GELU sets their speed.  erff() costs ~25 instructions; the forms below cost 10 (value)
+// and 17 (derivative), and the pair versions share one packed-FMA Horner chain (FFMA2,
+// fma.rn.f32x2 -- new on sm_100) between two arguments.
+//
+// value:       gelu(x) = relu(x) - t * 2^P(t),   t = min(|x|, 5.5),  P(t) ~ log2(Phi(-t))
+//              degree-6 P (tools/fit_gelu_log.py): max abs error 2.8e-7 vs erf-GELU in double
+//              (torch's own fp32 erf path is ~2e-7); beyond the clamp the true tail is < 1.1e-7.
+// derivative:  gelu'(x) = x < 0 ? m : 1 - m,      m = E * S(t),  E = exp(-t^2/2),
+//              S(t) = R(t) - t/sqrt(2 pi),  R(t) = Phi(-t) exp(t^2/2) ~ degree-9 polynomial
+//              (tools/fit_gelu.py): max abs error 8.7e-7.
+typedef unsigned long long f32x2;   // two packed floats in one 64-bit register pair
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
 {
-    float r = -6.306644367e-06f;
-    r = fmaf(r, t, 1.262593763e-04f);
-    r = fmaf(r, t, -1.118502270e-03f);
-    r = fmaf(r, t, 5.906143764e-03f);
-    r = fmaf(r, t, -2.138766862e-02f);
-    r = fmaf(r, t, 5.864728463e-02f);
-    r = fmaf(r, t, -1.313082752e-01f);
-    r = fmaf(r, t, 2.496296917e-01f);
-    r = fmaf(r, t, -3.989106504e-01f);
-    r = fmaf(r, t, 4.999995630e-01f);
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 splat2(float c) { return pack2(c, c); }
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -121,21 +129,97 @@ __device__ __forceinline__ float relu_nan(float x)
     return y;
 }
 
+#define AFR_GELU_T 5.5f
+#define AFR_P6 3.346384577e-05f
+#define AFR_P5 -7.723867644e-04f
+#define AFR_P4 8.091409570e-03f
+#define AFR_P3 -5.342996353e-02f
+#define AFR_P2 -4.587564624e-01f
+#define AFR_P1 -1.151206419e+00f
+#define AFR_P0 -9.999928108e-01f
+
 __device__ __forceinline__ float gelu_erf(float x)
 {
-    float t = fminf(fabsf(x), 5.5f);
-    float e = ex2_approx(t * t * -0.72134752044448170368f);   // exp(-t^2/2)
-    float w = t * e;
-    return fmaf(-w, gelu_poly_R(t), relu_nan(x));
+    const float t = fminf(fabsf(x), AFR_GELU_T);
+    float p = AFR_P6;
+    p = fmaf(p, t, AFR_P5);
+    p = fmaf(p, t, AFR_P4);
+    p = fmaf(p, t, AFR_P3);
+    p = fmaf(p, t, AFR_P2);
+    p = fmaf(p, t, AFR_P1);
+    p = fmaf(p, t, AFR_P0);
+    return fmaf(-t, ex2_approx(p), relu_nan(x));
 }
+
+// two GELUs, in place, sharing one FFMA2 Horner chain
+__device__ __forceinline__ void gelu_erf_x2(float &a, float &b)
+{
+    const float ta = fminf(fabsf(a), AFR_GELU_T), tb = fminf(fabsf(b), AFR_GELU_T);
+    const f32x2 t = pack2(ta, tb);
+    f32x2 p = splat2(AFR_P6);
+    p = fma2(p, t, splat2(AFR_P5));
+    p = fma2(p, t, splat2(AFR_P4));
+    p = fma2(p, t, splat2(AFR_P3));
+    p = fma2(p, t, splat2(AFR_P2));
+    p = fma2(p, t, splat2(AFR_P1));
+    p = fma2(p, t, splat2(AFR_P0));
+    float pa, pb;
+    unpack2(p, pa, pb);
+    a = fmaf(-ta, ex2_approx(pa), relu_nan(a));
+    b = fmaf(-tb, ex2_approx(pb), relu_nan(b));
+}
+
+#define AFR_S9 -6.306644367e-06f
+#define AFR_S8 1.262593763e-04f
+#define AFR_S7 -1.118502270e-03f
+#define AFR_S6 5.906143764e-03f
+#define AFR_S5 -2.138766862e-02f
+#define AFR_S4 5.864728463e-02f
+#define AFR_S3 -1.313082752e-01f
+#define AFR_S2 2.496296917e-01f
+#define AFR_S1 -7.978529308e-01f   /* R's linear term -3.989106504e-01 minus 1/sqrt(2 pi) */
+#define AFR_S0 4.999995630e-01f
+#define AFR_NHALF_LOG2E -0.72134752044448170368f
 
 __device__ __forceinline__ float gelu_erf_grad(float x)
 {
-    float t = fminf(fabsf(x), 5.5f);
-    float e = ex2_approx(t * t * -0.72134752044448170368f);
-    float er = e * gelu_poly_R(t);
-    float h = copysignf(0.5f - er, x);
-    return fmaf(x * e, 0.39894228040143267794f, 0.5f + h);
+    const float t = fminf(fabsf(x), AFR_GELU_T);
+    const float e = ex2_approx(t * t * AFR_NHALF_LOG2E);        // exp(-t^2/2)
+    float s = AFR_S9;
+    s = fmaf(s, t, AFR_S8);
+    s = fmaf(s, t, AFR_S7);
+    s = fmaf(s, t, AFR_S6);
+    s = fmaf(s, t, AFR_S5);
+    s = fmaf(s, t, AFR_S4);
+    s = fmaf(s, t, AFR_S3);
+    s = fmaf(s, t, AFR_S2);
+    s = fmaf(s, t, AFR_S1);
+    s = fmaf(s, t, AFR_S0);
+    const float m = e * s;
+    return x < 0.f ? m : 1.0f - m;
+}
+
+// (ga, gb) <- (gelu'(a) * ga, gelu'(b) * gb)
+__device__ __forceinline__ void gelu_erf_grad_mul_x2(float a, float b, float &ga, float &gb)
+{
+    const float ta = fminf(fabsf(a), AFR_GELU_T), tb = fminf(fabsf(b), AFR_GELU_T);
+    const float ea = ex2_approx(ta * ta * AFR_NHALF_LOG2E), eb = ex2_approx(tb * tb * AFR_NHALF_LOG2E);
+    const f32x2 t = pack2(ta, tb);
+    f32x2 s = splat2(AFR_S9);
+    s = fma2(s, t, splat2(AFR_S8));
+    s = fma2(s, t, splat2(AFR_S7));
+    s = fma2(s, t, splat2(AFR_S6));
+    s = fma2(s, t, splat2(AFR_S5));
+    s = fma2(s, t, splat2(AFR_S4));
+    s = fma2(s, t, splat2(AFR_S3));
+    s = fma2(s, t, splat2(AFR_S2));
+    s = fma2(s, t, splat2(AFR_S1));
+    s = fma2(s, t, splat2(AFR_S0));
+    float sa, sb;
+    unpack2(s, sa, sb);
+    const float ma = ea * sa, mb = eb * sb;
+    ga *= (a < 0.f ? ma : 1.0f - ma);
+    gb *= (b < 0.f ? mb : 1.0f - mb);
 }
 
 }  // namespace afr

@@ -6,6 +6,9 @@
 
 namespace afr {
 
+// Extra context for afr_last_error(), set by launchers when a step fails (thread local).
+void set_detail(const char *fmt, ...);
+
 // afr_generic.cu -- runtime-N kernels
 cudaError_t generic_up_like(const void *in, void *out, long planes, int Hin, int Win, int Hout,
                             int Wout, const TapsG &t, int in_dtype, int out_dtype, cudaStream_t s);

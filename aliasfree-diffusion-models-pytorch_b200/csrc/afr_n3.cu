@@ -57,43 +57,40 @@ __device__ __forceinline__ void up_odd_row(const float (&xa)[6], const float (&x
     }
 }
 
+// Activation on one mid row (startup row): 4 packed pairs + 1 scalar.
 template <bool kBwd>
-__device__ __forceinline__ void mid_even(const float (&xa)[6], const float (&da)[6],
-                                         const Taps3 &kU, const Taps3 &kG, bool first_col,
-                                         float (&m)[9])
+__device__ __forceinline__ void act_row(float (&u)[9], float (&g)[9])
 {
-    float u[9];
-    up_even_row(xa, kU, u);
     if (kBwd) {
-        float g[9];
-        up_even_row(da, kG, g);
 #pragma unroll
-        for (int c = 0; c < 9; ++c) m[c] = gelu_erf_grad(u[c]) * g[c];
+        for (int c = 1; c < 9; c += 2) gelu_erf_grad_mul_x2(u[c], u[c + 1], g[c], g[c + 1]);
+        g[0] *= gelu_erf_grad(u[0]);
     } else {
 #pragma unroll
-        for (int c = 0; c < 9; ++c) m[c] = gelu_erf(u[c]);
+        for (int c = 1; c < 9; c += 2) gelu_erf_x2(u[c], u[c + 1]);
+        u[0] = gelu_erf(u[0]);
     }
-    if (first_col) m[0] = 0.f;
 }
 
+// Activation on the two new mid rows of a step: 9 packed pairs (the two column-0 values pair up).
 template <bool kBwd>
-__device__ __forceinline__ void mid_odd(const float (&xa)[6], const float (&xb)[6],
-                                        const float (&da)[6], const float (&db)[6],
-                                        const Taps3 &kU, const Taps3 &kG, bool first_col,
-                                        float (&m)[9])
+__device__ __forceinline__ void act_rows(float (&ue)[9], float (&uo)[9], float (&ge)[9], float (&go)[9])
 {
-    float u[9];
-    up_odd_row(xa, xb, kU, u);
     if (kBwd) {
-        float g[9];
-        up_odd_row(da, db, kG, g);
 #pragma unroll
-        for (int c = 0; c < 9; ++c) m[c] = gelu_erf_grad(u[c]) * g[c];
+        for (int c = 1; c < 9; c += 2) {
+            gelu_erf_grad_mul_x2(ue[c], ue[c + 1], ge[c], ge[c + 1]);
+            gelu_erf_grad_mul_x2(uo[c], uo[c + 1], go[c], go[c + 1]);
+        }
+        gelu_erf_grad_mul_x2(ue[0], uo[0], ge[0], go[0]);
     } else {
 #pragma unroll
-        for (int c = 0; c < 9; ++c) m[c] = gelu_erf(u[c]);
+        for (int c = 1; c < 9; c += 2) {
+            gelu_erf_x2(ue[c], ue[c + 1]);
+            gelu_erf_x2(uo[c], uo[c + 1]);
+        }
+        gelu_erf_x2(ue[0], uo[0]);
     }
-    if (first_col) m[0] = 0.f;
 }
 
 // ---------------------------------------------------------------------------------
@@ -152,44 +149,65 @@ __device__ __forceinline__ void strip_core(const SX &sx, const SD &sd, TO *__res
                                            int i0, int i1, bool first_col, const Taps3 &kU,
                                            const Taps3 &kG, const Taps3 &kB)
 {
-    float xa[6], xb[6], da[6], db[6], gp[9];
+    // fwd: m* hold gelu(u).  bwd: m* hold dg, then gelu'(u) * dg.
+    float xa[6], xb[6], da[6], db[6], mp[9];
 #pragma unroll
     for (int c = 0; c < 6; ++c) { da[c] = 0.f; db[c] = 0.f; }
     sx.load(i0, xb);
     if (kBwd) sd.load(i0, db);
     if (i0 > 0) {
+        float u[9];
         sx.load(i0 - 1, xa);
-        if (kBwd) sd.load(i0 - 1, da);
-        mid_odd<kBwd>(xa, xb, da, db, kU, kG, first_col, gp);
+        up_odd_row(xa, xb, kU, u);
+        if (kBwd) {
+            sd.load(i0 - 1, da);
+            up_odd_row(da, db, kG, mp);
+            act_row<true>(u, mp);
+        } else {
+            act_row<false>(u, u);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) mp[c] = u[c];
+        }
+        if (first_col) mp[0] = 0.f;
     } else {
 #pragma unroll
-        for (int c = 0; c < 9; ++c) gp[c] = 0.f;
+        for (int c = 0; c < 9; ++c) mp[c] = 0.f;
     }
     for (int i = i0; i < i1; ++i) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) { xa[c] = xb[c]; da[c] = db[c]; }
         sx.load(i + 1, xb);
         if (kBwd) sd.load(i + 1, db);
-        float ge[9], go[9];
-        mid_even<kBwd>(xa, da, kU, kG, first_col, ge);
-        mid_odd<kBwd>(xa, xb, da, db, kU, kG, first_col, go);
+        float ue[9], uo[9], me[9], mo[9];
+        up_even_row(xa, kU, ue);
+        up_odd_row(xa, xb, kU, uo);
+        if (kBwd) {
+            up_even_row(da, kG, me);
+            up_odd_row(da, db, kG, mo);
+            act_rows<true>(ue, uo, me, mo);
+        } else {
+            act_rows<false>(ue, uo, ue, uo);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) { me[c] = ue[c]; mo[c] = uo[c]; }
+        }
+        if (first_col) { me[0] = 0.f; mo[0] = 0.f; }
         float o[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float acc = kB.k[0][0] * gp[2 * q];
-            acc = fmaf(kB.k[0][1], gp[2 * q + 1], acc);
-            acc = fmaf(kB.k[0][2], gp[2 * q + 2], acc);
-            acc = fmaf(kB.k[1][0], ge[2 * q], acc);
-            acc = fmaf(kB.k[1][1], ge[2 * q + 1], acc);
-            acc = fmaf(kB.k[1][2], ge[2 * q + 2], acc);
-            acc = fmaf(kB.k[2][0], go[2 * q], acc);
-            acc = fmaf(kB.k[2][1], go[2 * q + 1], acc);
-            acc = fmaf(kB.k[2][2], go[2 * q + 2], acc);
+            float acc = kB.k[0][0] * mp[2 * q];
+            acc = fmaf(kB.k[0][1], mp[2 * q + 1], acc);
+            acc = fmaf(kB.k[0][2], mp[2 * q + 2], acc);
+            acc = fmaf(kB.k[1][0], me[2 * q], acc);
+            acc = fmaf(kB.k[1][1], me[2 * q + 1], acc);
+            acc = fmaf(kB.k[1][2], me[2 * q + 2], acc);
+            acc = fmaf(kB.k[2][0], mo[2 * q], acc);
+            acc = fmaf(kB.k[2][1], mo[2 * q + 1], acc);
+            acc = fmaf(kB.k[2][2], mo[2 * q + 2], acc);
             o[q] = acc;
         }
         st4(out + (long)i * W, make_float4(o[0], o[1], o[2], o[3]));
 #pragma unroll
-        for (int c = 0; c < 9; ++c) gp[c] = go[c];
+        for (int c = 0; c < 9; ++c) mp[c] = mo[c];
     }
 }
 
@@ -262,6 +280,10 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
+// Column halo of the staged tile, in elements: 16 bytes on each side, so that the box start
+// (j0 - halo) stays 16-byte aligned in global memory for fp32 (4) and bf16 (8) alike.
+template <typename T> struct Halo { static constexpr int value = 16 / (int)sizeof(T); };
+
 struct TileCfg {
     int Tw, Th, P, R;          // tile width/height (outputs), planes per tile, rows per thread
     int strips, nseg;          // Tw/4, Th/R
@@ -284,7 +306,8 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     const int ty = (int)(bid % cfg.tiles_y);
     const long p0 = (bid / cfg.tiles_y) * cfg.P;
     const int j0 = tx * cfg.Tw, it0 = ty * cfg.Th;
-    const int pitch = cfg.Tw + 8, rows = cfg.Th + 2;
+    constexpr int HALO = Halo<T>::value;
+    const int pitch = cfg.Tw + 2 * HALO, rows = cfg.Th + 2;
 
     T *xs = reinterpret_cast<T *>(tile_smem);
     T *rs = reinterpret_cast<T *>(tile_smem + (kRes ? cfg.tile_bytes : 0));
@@ -298,9 +321,9 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     if (threadIdx.x == 0) {
         const uint32_t box_bytes = (uint32_t)(pitch * rows * cfg.P * sizeof(T));
         mbar_expect_tx(&bar, box_bytes * (1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0)));
-        tma_load_3d(xs, &mx, &bar, j0 - 4, it0 - 1, (int)p0);
-        if (kRes) tma_load_3d(rs, &mres, &bar, j0 - 4, it0 - 1, (int)p0);
-        if (kBwd) tma_load_3d(ds, &mdy, &bar, j0 - 4, it0 - 1, (int)p0);
+        tma_load_3d(xs, &mx, &bar, j0 - HALO, it0 - 1, (int)p0);
+        if (kRes) tma_load_3d(rs, &mres, &bar, j0 - HALO, it0 - 1, (int)p0);
+        if (kBwd) tma_load_3d(ds, &mdy, &bar, j0 - HALO, it0 - 1, (int)p0);
     }
 
     const int s = threadIdx.x % cfg.strips;
@@ -315,7 +338,7 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     mbar_wait(&bar, 0);
     if (!active) return;
 
-    const int toff = pl * rows * pitch + 4 + 4 * s;
+    const int toff = pl * rows * pitch + HALO + 4 * s;
     TileRows<T, kRes> sx{xs + toff, rs + toff, pitch, it0 - 1};
     TileRows<T, false> sd{ds + toff, nullptr, pitch, it0 - 1};
     strip_core<kBwd>(sx, sd, out + p * (long)H * W + j, W, i0, i1, j == 0, kU, kG, kB);
@@ -483,16 +506,26 @@ static bool make_plane_map(CUtensorMap *m, const void *base, long planes, int H,
                            int box_w, int box_h, int box_p)
 {
     EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) return false;
+    if (!enc) { set_detail("cuTensorMapEncodeTiled entry point not found"); return false; }
     const size_t es = esize(dtype);
     cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)W * es, (cuuint64_t)W * H * es};
     cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_p};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(m, dtype == AFR_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                     3, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = CUDA_SUCCESS;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        r = enc(m, dtype == AFR_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+        // A thread that has made no runtime call yet (e.g. PyTorch's autograd worker on its first
+        // backward) has no context bound for this driver-API call: bind the primary context.
+        cudaFree(0);
+    }
+    if (r != CUDA_SUCCESS)
+        set_detail("cuTensorMapEncodeTiled failed (CUresult %d) base=%p dims=[%d,%d,%ld] box=[%d,%d,%d]", (int)r,
+                   base, W, H, planes, box_w, box_h, box_p);
     return r == CUDA_SUCCESS;
 }
 
@@ -529,7 +562,7 @@ static bool pick_tile(int H, int W, int dtype, int ntiles, int *threads, TileCfg
         c.Th = c.nseg * c.R;
         c.tiles_x = (W + c.Tw - 1) / c.Tw;
         c.tiles_y = (H + c.Th - 1) / c.Th;
-        size_t bytes = (size_t)(c.Tw + 8) * (c.Th + 2) * c.P * es;
+        size_t bytes = (size_t)(c.Tw + 2 * (16 / es)) * (c.Th + 2) * c.P * es;
         c.tile_bytes = (int)((bytes + 127) / 128 * 128);
         if (c.P > 256 || c.Th + 2 > 256) continue;
         if ((size_t)c.tile_bytes * ntiles <= 48 * 1024 || th == 64) {
@@ -548,12 +581,13 @@ static cudaError_t launch_tma(const void *x, const void *res, const void *dy, vo
 {
     const int ntiles = 1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0);
     int threads; TileCfg cfg;
-    if (!pick_tile(H, W, dtype, ntiles, &threads, &cfg)) return cudaErrorInvalidConfiguration;
+    if (!pick_tile(H, W, dtype, ntiles, &threads, &cfg)) { set_detail("no tile configuration"); return cudaErrorInvalidConfiguration; }
     CUtensorMap mx, mres, mdy;
-    if (!make_plane_map(&mx, x, planes, H, W, dtype, cfg.Tw + 8, cfg.Th + 2, cfg.P)) return cudaErrorNotSupported;
+    const int bw = cfg.Tw + 2 * Halo<T>::value, bh = cfg.Th + 2;
+    if (!make_plane_map(&mx, x, planes, H, W, dtype, bw, bh, cfg.P)) return cudaErrorInvalidValue;
     mres = mx; mdy = mx;
-    if (kRes && !make_plane_map(&mres, res, planes, H, W, dtype, cfg.Tw + 8, cfg.Th + 2, cfg.P)) return cudaErrorNotSupported;
-    if (kBwd && !make_plane_map(&mdy, dy, planes, H, W, dtype, cfg.Tw + 8, cfg.Th + 2, cfg.P)) return cudaErrorNotSupported;
+    if (kRes && !make_plane_map(&mres, res, planes, H, W, dtype, bw, bh, cfg.P)) return cudaErrorInvalidValue;
+    if (kBwd && !make_plane_map(&mdy, dy, planes, H, W, dtype, bw, bh, cfg.P)) return cudaErrorInvalidValue;
     const long pgroups = (planes + cfg.P - 1) / cfg.P;
     const long grid = pgroups * cfg.tiles_x * cfg.tiles_y;
     if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
@@ -562,11 +596,14 @@ static cudaError_t launch_tma(const void *x, const void *res, const void *dy, vo
     static bool attr_set = false;     // per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
+        if (e != cudaSuccess) { set_detail("cudaFuncSetAttribute(max dynamic smem) failed"); return e; }
         attr_set = true;
     }
     kern<<<(unsigned)grid, threads, smem, s>>>(mx, mres, mdy, (T *)out, planes, H, W, cfg, kU, kG, kB);
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        set_detail("launch grid=%ld block=%d smem=%zu tile Tw=%d Th=%d P=%d", grid, threads, smem, cfg.Tw, cfg.Th, cfg.P);
+    return e;
 }
 
 cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, void *out, long planes, int H,

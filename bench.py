@@ -359,10 +359,16 @@ def main():
         out["cpu_baseline"] = None
     if not args.no_sweep and ws == 1:
         torch.cuda.empty_cache()
-        out["sweep"] = sweep(afr, quick=not args.full_sweep)
+        try:
+            out["sweep"] = sweep(afr, quick=not args.full_sweep)
+        except Exception as e:                      # never lose the headline to a side table
+            out["sweep"] = {"error": repr(e)[:300]}
     if not args.no_ddpm:
         torch.cuda.empty_cache()
-        out["ddpm_v3"] = ddpm_v3(afr, ws, rank, args.ddpm_batch, steps=min(args.steps, 5), warmup=3)
+        try:
+            out["ddpm_v3"] = ddpm_v3(afr, ws, rank, args.ddpm_batch, steps=min(args.steps, 5), warmup=3)
+        except Exception as e:
+            out["ddpm_v3"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(out))
     if ws > 1:
