@@ -32,20 +32,23 @@ namespace afr {
 // mid-row arithmetic
 // ---------------------------------------------------------------------------------
 // 9 columns m = 0..8  <->  X = 2j-1+m.  xa/xb hold input columns j-1 .. j+4.
-__device__ __forceinline__ void up_even_row(const float (&xa)[6], const Taps3 &k, float (&u)[9])
+// Column 0 is kept separate from columns 1..8: in shuffle mode it usually comes from lane-1.
+template <int M0>
+__device__ __forceinline__ void up_even_cols(const float (&xa)[6], const Taps3 &k, float (&u)[9])
 {
 #pragma unroll
-    for (int m = 0; m < 9; ++m) {
+    for (int m = M0; m < (M0 == 0 ? 1 : 9); ++m) {
         if (m & 1) u[m] = k.k[1][1] * xa[(m + 1) / 2];
         else u[m] = fmaf(k.k[1][2], xa[m / 2 + 1], k.k[1][0] * xa[m / 2]);
     }
 }
 
-__device__ __forceinline__ void up_odd_row(const float (&xa)[6], const float (&xb)[6],
-                                           const Taps3 &k, float (&u)[9])
+template <int M0>
+__device__ __forceinline__ void up_odd_cols(const float (&xa)[6], const float (&xb)[6],
+                                            const Taps3 &k, float (&u)[9])
 {
 #pragma unroll
-    for (int m = 0; m < 9; ++m) {
+    for (int m = M0; m < (M0 == 0 ? 1 : 9); ++m) {
         if (m & 1) {
             u[m] = fmaf(k.k[2][1], xb[(m + 1) / 2], k.k[0][1] * xa[(m + 1) / 2]);
         } else {
@@ -57,40 +60,31 @@ __device__ __forceinline__ void up_odd_row(const float (&xa)[6], const float (&x
     }
 }
 
-// Activation on one mid row (startup row): 4 packed pairs + 1 scalar.
+// Activation on the mid rows.  fwd: u <- gelu(u) in place (g is unused, pass u twice).
+// bwd: g <- gelu'(u) * g.  Columns 1..8 form packed pairs; column 0 (X = 2j-1) is separate
+// because in shuffle mode it is normally taken from the left neighbour's column 8.
 template <bool kBwd>
-__device__ __forceinline__ void act_row(float (&u)[9], float (&g)[9])
+__device__ __forceinline__ void act_cols_1_8(float (&u)[9], float (&g)[9])
 {
-    if (kBwd) {
 #pragma unroll
-        for (int c = 1; c < 9; c += 2) gelu_erf_grad_mul_x2(u[c], u[c + 1], g[c], g[c + 1]);
-        g[0] *= gelu_erf_grad(u[0]);
-    } else {
-#pragma unroll
-        for (int c = 1; c < 9; c += 2) gelu_erf_x2(u[c], u[c + 1]);
-        u[0] = gelu_erf(u[0]);
+    for (int c = 1; c < 9; c += 2) {
+        if (kBwd) gelu_erf_grad_mul_x2(u[c], u[c + 1], g[c], g[c + 1]);
+        else gelu_erf_x2(u[c], u[c + 1]);
     }
 }
 
-// Activation on the two new mid rows of a step: 9 packed pairs (the two column-0 values pair up).
 template <bool kBwd>
-__device__ __forceinline__ void act_rows(float (&ue)[9], float (&uo)[9], float (&ge)[9], float (&go)[9])
+__device__ __forceinline__ void act_col0_single(float (&u)[9], float (&g)[9])
 {
-    if (kBwd) {
-#pragma unroll
-        for (int c = 1; c < 9; c += 2) {
-            gelu_erf_grad_mul_x2(ue[c], ue[c + 1], ge[c], ge[c + 1]);
-            gelu_erf_grad_mul_x2(uo[c], uo[c + 1], go[c], go[c + 1]);
-        }
-        gelu_erf_grad_mul_x2(ue[0], uo[0], ge[0], go[0]);
-    } else {
-#pragma unroll
-        for (int c = 1; c < 9; c += 2) {
-            gelu_erf_x2(ue[c], ue[c + 1]);
-            gelu_erf_x2(uo[c], uo[c + 1]);
-        }
-        gelu_erf_x2(ue[0], uo[0]);
-    }
+    if (kBwd) g[0] *= gelu_erf_grad(u[0]);
+    else u[0] = gelu_erf(u[0]);
+}
+
+template <bool kBwd>
+__device__ __forceinline__ void act_col0_pair(float (&ue)[9], float (&uo)[9], float (&ge)[9], float (&go)[9])
+{
+    if (kBwd) gelu_erf_grad_mul_x2(ue[0], uo[0], ge[0], go[0]);
+    else gelu_erf_x2(ue[0], uo[0]);
 }
 
 // ---------------------------------------------------------------------------------
@@ -144,71 +138,125 @@ struct TileRows {
 // ---------------------------------------------------------------------------------
 // the strip core
 // ---------------------------------------------------------------------------------
+// One output row.  In: xa/da = input rows i (x / dy), mp = mid row 2i-1.  Loads rows i+1 into
+// xb/db, evaluates mid rows 2i (local) and 2i+1 (-> mo), stores out[i][j..j+3] if `store`.
+//
+// Column 0 of every mid row (X = 2j-1) is the same sample as column 8 of the thread one strip to
+// the left, so it is fetched from lane-1 with a shuffle instead of being recomputed: 16 GELUs per
+// step instead of 18.  Every lane of the warp therefore runs every step (lanes without real work
+// run on safe coordinates with `store` off).  `own0` marks the lanes whose left neighbour is not
+// lane-1 (first strip of a later column tile, or lane 0 when the strip count does not divide 32);
+// they compute column 0 themselves in a short divergent branch.
+template <bool kBwd, class SX, class SD, typename TO>
+__device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__restrict__ out, int W, int i,
+                                           bool store, bool first_col, bool own0, const Taps3 &kU,
+                                           const Taps3 &kG, const Taps3 &kB, const float (&xa)[6],
+                                           float (&xb)[6], const float (&da)[6], float (&db)[6],
+                                           const float (&mp)[9], float (&mo)[9])
+{
+    sx.load(i + 1, xb);
+    if (kBwd) sd.load(i + 1, db);
+    float me[9];
+    if (kBwd) {
+        float ue[9], uo[9];
+        up_even_cols<1>(xa, kU, ue);
+        up_odd_cols<1>(xa, xb, kU, uo);
+        up_even_cols<1>(da, kG, me);
+        up_odd_cols<1>(da, db, kG, mo);
+        act_cols_1_8<true>(ue, me);
+        act_cols_1_8<true>(uo, mo);
+        if (own0) {
+            up_even_cols<0>(xa, kU, ue);
+            up_odd_cols<0>(xa, xb, kU, uo);
+            up_even_cols<0>(da, kG, me);
+            up_odd_cols<0>(da, db, kG, mo);
+            act_col0_pair<true>(ue, uo, me, mo);
+        }
+    } else {
+        up_even_cols<1>(xa, kU, me);
+        up_odd_cols<1>(xa, xb, kU, mo);
+        act_cols_1_8<false>(me, me);
+        act_cols_1_8<false>(mo, mo);
+        if (own0) {
+            up_even_cols<0>(xa, kU, me);
+            up_odd_cols<0>(xa, xb, kU, mo);
+            act_col0_pair<false>(me, mo, me, mo);
+        }
+    }
+    const float le = __shfl_up_sync(0xffffffffu, me[8], 1), lo = __shfl_up_sync(0xffffffffu, mo[8], 1);
+    if (!own0) { me[0] = le; mo[0] = lo; }
+    if (first_col) { me[0] = 0.f; mo[0] = 0.f; }
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float acc = kB.k[0][0] * mp[2 * q];
+        acc = fmaf(kB.k[0][1], mp[2 * q + 1], acc);
+        acc = fmaf(kB.k[0][2], mp[2 * q + 2], acc);
+        acc = fmaf(kB.k[1][0], me[2 * q], acc);
+        acc = fmaf(kB.k[1][1], me[2 * q + 1], acc);
+        acc = fmaf(kB.k[1][2], me[2 * q + 2], acc);
+        acc = fmaf(kB.k[2][0], mo[2 * q], acc);
+        acc = fmaf(kB.k[2][1], mo[2 * q + 1], acc);
+        acc = fmaf(kB.k[2][2], mo[2 * q + 2], acc);
+        o[q] = acc;
+    }
+    if (store) st4(out + (long)i * W, make_float4(o[0], o[1], o[2], o[3]));
+}
+
+// R steps starting at row i0 (R is warp-uniform); rows >= i1 are computed but not stored.
 template <bool kBwd, class SX, class SD, typename TO>
 __device__ __forceinline__ void strip_core(const SX &sx, const SD &sd, TO *__restrict__ out, int W,
-                                           int i0, int i1, bool first_col, const Taps3 &kU,
-                                           const Taps3 &kG, const Taps3 &kB)
+                                           int i0, int i1, int R, bool valid, bool first_col, bool own0,
+                                           const Taps3 &kU, const Taps3 &kG, const Taps3 &kB)
 {
-    // fwd: m* hold gelu(u).  bwd: m* hold dg, then gelu'(u) * dg.
-    float xa[6], xb[6], da[6], db[6], mp[9];
+    // two register sets used ping-pong so that "row i+1 becomes row i" costs no moves
+    float x0[6], x1[6], d0[6], d1[6], m0[9], m1[9];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { da[c] = 0.f; db[c] = 0.f; }
-    sx.load(i0, xb);
-    if (kBwd) sd.load(i0, db);
-    if (i0 > 0) {
+    for (int c = 0; c < 6; ++c) { d0[c] = 0.f; d1[c] = 0.f; }
+    sx.load(i0, x0);
+    if (kBwd) sd.load(i0, d0);
+    // mid row 2*i0-1.  The branch is warp-uniform (a warp that holds both a first and a later
+    // row segment computes it on all lanes and zeroes it below) so that the warp stays converged
+    // for the shuffles; planes that fit one segment (4x4, 8x8) skip it altogether.
+    if (__any_sync(0xffffffffu, i0 > 0)) {
+    sx.load(i0 - 1, x1);
+    if (kBwd) {
         float u[9];
-        sx.load(i0 - 1, xa);
-        up_odd_row(xa, xb, kU, u);
-        if (kBwd) {
-            sd.load(i0 - 1, da);
-            up_odd_row(da, db, kG, mp);
-            act_row<true>(u, mp);
-        } else {
-            act_row<false>(u, u);
-#pragma unroll
-            for (int c = 0; c < 9; ++c) mp[c] = u[c];
+        sd.load(i0 - 1, d1);
+        up_odd_cols<1>(x1, x0, kU, u);
+        up_odd_cols<1>(d1, d0, kG, m0);
+        act_cols_1_8<true>(u, m0);
+        if (own0) {
+            up_odd_cols<0>(x1, x0, kU, u);
+            up_odd_cols<0>(d1, d0, kG, m0);
+            act_col0_single<true>(u, m0);
         }
-        if (first_col) mp[0] = 0.f;
     } else {
-#pragma unroll
-        for (int c = 0; c < 9; ++c) mp[c] = 0.f;
-    }
-    for (int i = i0; i < i1; ++i) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { xa[c] = xb[c]; da[c] = db[c]; }
-        sx.load(i + 1, xb);
-        if (kBwd) sd.load(i + 1, db);
-        float ue[9], uo[9], me[9], mo[9];
-        up_even_row(xa, kU, ue);
-        up_odd_row(xa, xb, kU, uo);
-        if (kBwd) {
-            up_even_row(da, kG, me);
-            up_odd_row(da, db, kG, mo);
-            act_rows<true>(ue, uo, me, mo);
-        } else {
-            act_rows<false>(ue, uo, ue, uo);
-#pragma unroll
-            for (int c = 0; c < 9; ++c) { me[c] = ue[c]; mo[c] = uo[c]; }
+        up_odd_cols<1>(x1, x0, kU, m0);
+        act_cols_1_8<false>(m0, m0);
+        if (own0) {
+            up_odd_cols<0>(x1, x0, kU, m0);
+            act_col0_single<false>(m0, m0);
         }
-        if (first_col) { me[0] = 0.f; mo[0] = 0.f; }
-        float o[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float acc = kB.k[0][0] * mp[2 * q];
-            acc = fmaf(kB.k[0][1], mp[2 * q + 1], acc);
-            acc = fmaf(kB.k[0][2], mp[2 * q + 2], acc);
-            acc = fmaf(kB.k[1][0], me[2 * q], acc);
-            acc = fmaf(kB.k[1][1], me[2 * q + 1], acc);
-            acc = fmaf(kB.k[1][2], me[2 * q + 2], acc);
-            acc = fmaf(kB.k[2][0], mo[2 * q], acc);
-            acc = fmaf(kB.k[2][1], mo[2 * q + 1], acc);
-            acc = fmaf(kB.k[2][2], mo[2 * q + 2], acc);
-            o[q] = acc;
-        }
-        st4(out + (long)i * W, make_float4(o[0], o[1], o[2], o[3]));
-#pragma unroll
-        for (int c = 0; c < 9; ++c) mp[c] = mo[c];
     }
+    {
+        const float l = __shfl_up_sync(0xffffffffu, m0[8], 1);
+        if (!own0) m0[0] = l;
+    }
+    if (first_col) m0[0] = 0.f;
+    }
+    if (i0 == 0) {                                  // row -1 lies outside the 2x grid: mid == 0
+#pragma unroll
+        for (int c = 0; c < 9; ++c) m0[c] = 0.f;
+    }
+    const int iend = i0 + R;
+    int i = i0;
+    for (; i + 1 < iend; i += 2) {
+        strip_step<kBwd>(sx, sd, out, W, i, valid && i < i1, first_col, own0, kU, kG, kB, x0, x1, d0, d1, m0, m1);
+        strip_step<kBwd>(sx, sd, out, W, i + 1, valid && i + 1 < i1, first_col, own0, kU, kG, kB, x1, x0, d1, d0, m1, m0);
+    }
+    if (i < iend)
+        strip_step<kBwd>(sx, sd, out, W, i, valid && i < i1, first_col, own0, kU, kG, kB, x0, x1, d0, d1, m0, m1);
 }
 
 // ---------------------------------------------------------------------------------
@@ -221,9 +269,10 @@ fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T
                      const __grid_constant__ Taps3 kU, const __grid_constant__ Taps3 kG,
                      const __grid_constant__ Taps3 kB)
 {
-    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const long per_plane = (long)strips * nseg;
-    if (idx >= planes * per_plane) return;
+    const bool valid = idx < planes * per_plane;
+    if (!valid) idx = 0;                           // idle lanes shadow thread 0, stores off
     const int s = (int)(idx % strips);
     const int seg = (int)((idx / strips) % nseg);
     const long p = idx / per_plane;
@@ -231,7 +280,8 @@ fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T
     const long base = p * (long)H * W + j;
     GlobalRows<T, kRes> sx{x + base, kRes ? res + base : nullptr, H, W, j};
     GlobalRows<T, false> sd{kBwd ? dy + base : nullptr, nullptr, H, W, j};
-    strip_core<kBwd>(sx, sd, out + base, W, i0, i1, j == 0, kU, kG, kB);
+    const bool own0 = (s > 0) && ((threadIdx.x & 31) == 0);
+    strip_core<kBwd>(sx, sd, out + base, W, i0, i1, R, valid, j == 0, own0, kU, kG, kB);
 }
 
 // ---------------------------------------------------------------------------------
@@ -328,20 +378,22 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
 
     const int s = threadIdx.x % cfg.strips;
     const int q = threadIdx.x / cfg.strips;
-    const int pl = q % cfg.P, seg = q / cfg.P;
-    const long p = p0 + pl;
+    int pl = q % cfg.P, seg = q / cfg.P;
     const int j = j0 + 4 * s;
+    const bool valid = (seg < cfg.nseg) && (p0 + pl < planes) && (j < W);
+    if (seg >= cfg.nseg) { pl = 0; seg = 0; }      // idle lanes read a valid part of the tile, stores off
+    const long p = p0 + pl;
     const int i0 = it0 + seg * cfg.R;
     const int i1 = min(min(H, it0 + cfg.Th), i0 + cfg.R);
-    const bool active = (seg < cfg.nseg) && (p < planes) && (j < W) && (i0 < i1);
 
     mbar_wait(&bar, 0);
-    if (!active) return;
 
     const int toff = pl * rows * pitch + HALO + 4 * s;
     TileRows<T, kRes> sx{xs + toff, rs + toff, pitch, it0 - 1};
     TileRows<T, false> sd{ds + toff, nullptr, pitch, it0 - 1};
-    strip_core<kBwd>(sx, sd, out + p * (long)H * W + j, W, i0, i1, j == 0, kU, kG, kB);
+    T *dst = out + p * (long)H * W + j;
+    const bool own0 = (j > 0) && (s == 0 || (threadIdx.x & 31) == 0);
+    strip_core<kBwd>(sx, sd, dst, W, i0, i1, cfg.R, valid, j == 0, own0, kU, kG, kB);
 }
 
 // ---------------------------------------------------------------------------------
