@@ -252,7 +252,7 @@ static int fused_common(const void *x, const void *residual, const void *dy, voi
     const int path = current_path();
     const void *ptrs[4] = {x, residual, bwd ? dy : nullptr, out};
     if (N_up == 3 && N_down == 3 && path != AFR_PATH_GENERIC && n3_fgelu_supported(H, W, ptrs, 4, dtype)) {
-        const bool tma_ok = n3_fgelu_tma_supported(H, W, ptrs, 4, dtype);
+        const bool tma_ok = n3_fgelu_tma_supported(planes, H, W, ptrs, 4, dtype, 1 + (residual ? 1 : 0) + (bwd ? 1 : 0));
         if (path == AFR_PATH_TMA && !tma_ok)
             return fail(AFR_ERR_UNSUPPORTED, "TMA path forced but shape/alignment not eligible (H=%d W=%d)", H, W);
         const bool use_tma = (path == AFR_PATH_TMA) || (path == AFR_PATH_AUTO && tma_ok);

@@ -21,7 +21,8 @@ cudaError_t generic_fgelu(const void *x, const void *res, const void *dy, void *
 // afr_n3.cu -- N == 3 register-strip kernels (direct and TMA-staged)
 // All take stage taps already arranged for the stencil they run (see afr_api.cu).
 bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype);
-bool n3_fgelu_tma_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype);
+bool n3_fgelu_tma_supported(long planes, int H, int W, const void *const *ptrs, int nptrs, int dtype,
+                            int n_inputs);
 cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, void *out, long planes,
                      int H, int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd,
                      int dtype, bool use_tma, cudaStream_t s, const char **kernel_name);

@@ -18,10 +18,12 @@
 // Two data paths feed the same core:
 //   direct  rows are read from global memory (128-bit loads + two scalars, L1-cached),
 //           used for tiny planes (4x4, 8x8) and shapes TMA cannot describe;
-//   tma     one elected thread issues cp.async.bulk.tensor (3-D box [Tw+8, Th+2, P planes],
-//           out-of-bounds zero fill = the conv's zero padding) into shared memory and the
-//           CTA waits on an mbarrier; rows then come from the staged tile.
+//   tma     row-streaming: a CTA owns P planes x one column tile for the whole plane height; one
+//           elected thread keeps a 2-stage ring of cp.async.bulk.tensor boxes
+//           [Tw + 2*halo, R+1 rows, P planes] in flight (out-of-bounds zero fill = the conv's
+//           zero padding, mbarrier complete_tx), threads read rows from the staged chunk.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "afr_common.cuh"
 #include "afr_kernels.h"
@@ -334,66 +336,95 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 // (j0 - halo) stays 16-byte aligned in global memory for fp32 (4) and bf16 (8) alike.
 template <typename T> struct Halo { static constexpr int value = 16 / (int)sizeof(T); };
 
+// Row-streaming tile configuration: a CTA owns P planes x one column tile of Tw outputs and
+// walks down ALL rows of those planes in chunks of R rows; chunk k is the box
+// [Tw + 2*halo, R + 1 rows (kR .. kR+R), P planes] and lands in stage k & 1.
 struct TileCfg {
-    int Tw, Th, P, R;          // tile width/height (outputs), planes per tile, rows per thread
-    int strips, nseg;          // Tw/4, Th/R
-    int tiles_x, tiles_y;
-    int tile_bytes;            // bytes of one staged tile, rounded up to 128
+    int Tw, R, P;              // tile width (outputs), rows per chunk, planes per CTA
+    int strips;                // Tw / 4 : threads per plane row
+    int tiles_x, nchunks;      // column tiles per plane, row chunks per plane
+    int tile_bytes;            // bytes of one staged box, rounded up to 128
 };
 
+// Each thread keeps its 4-column strip of one plane for the whole plane height: the carried
+// mid row and input row simply stay in registers across chunks, so there is no per-segment
+// start-up work at all, and the next two chunks are always in flight (2-stage TMA/mbarrier
+// ring) while the current one is being computed.
 template <typename T, bool kBwd, bool kRes>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mres,
                   const __grid_constant__ CUtensorMap mdy, T *__restrict__ out, long planes, int H,
                   int W, const __grid_constant__ TileCfg cfg, const __grid_constant__ Taps3 kU,
                   const __grid_constant__ Taps3 kG, const __grid_constant__ Taps3 kB)
 {
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    __shared__ __align__(8) uint64_t bar;
-
-    long bid = blockIdx.x;
-    const int tx = (int)(bid % cfg.tiles_x); bid /= cfg.tiles_x;
-    const int ty = (int)(bid % cfg.tiles_y);
-    const long p0 = (bid / cfg.tiles_y) * cfg.P;
-    const int j0 = tx * cfg.Tw, it0 = ty * cfg.Th;
+    __shared__ __align__(8) uint64_t full[2];
     constexpr int HALO = Halo<T>::value;
-    const int pitch = cfg.Tw + 2 * HALO, rows = cfg.Th + 2;
+    constexpr int NIN = 1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0);
 
-    T *xs = reinterpret_cast<T *>(tile_smem);
-    T *rs = reinterpret_cast<T *>(tile_smem + (kRes ? cfg.tile_bytes : 0));
-    T *ds = reinterpret_cast<T *>(tile_smem + (kRes ? 2 : 1) * cfg.tile_bytes);
+    const int tx = (int)(blockIdx.x % cfg.tiles_x);
+    const long p0 = (long)(blockIdx.x / cfg.tiles_x) * cfg.P;
+    const int j0 = tx * cfg.Tw;
+    const int pitch = cfg.Tw + 2 * HALO, rows = cfg.R + 1;
+    const int stage_bytes = NIN * cfg.tile_bytes;
+    const uint32_t box_bytes = (uint32_t)(pitch * rows * cfg.P * sizeof(T));
+
+    auto issue = [&](int k) {          // one thread: arm the stage's barrier, launch its boxes
+        unsigned char *base = tile_smem + (k & 1) * stage_bytes;
+        uint64_t *bar = &full[k & 1];
+        mbar_expect_tx(bar, box_bytes * NIN);
+        tma_load_3d(base, &mx, bar, j0 - HALO, k * cfg.R, (int)p0);
+        if (kRes) tma_load_3d(base + cfg.tile_bytes, &mres, bar, j0 - HALO, k * cfg.R, (int)p0);
+        if (kBwd) tma_load_3d(base + (kRes ? 2 : 1) * cfg.tile_bytes, &mdy, bar, j0 - HALO, k * cfg.R, (int)p0);
+    };
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t box_bytes = (uint32_t)(pitch * rows * cfg.P * sizeof(T));
-        mbar_expect_tx(&bar, box_bytes * (1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0)));
-        tma_load_3d(xs, &mx, &bar, j0 - HALO, it0 - 1, (int)p0);
-        if (kRes) tma_load_3d(rs, &mres, &bar, j0 - HALO, it0 - 1, (int)p0);
-        if (kBwd) tma_load_3d(ds, &mdy, &bar, j0 - HALO, it0 - 1, (int)p0);
+        issue(0);
+        if (cfg.nchunks > 1) issue(1);
     }
 
     const int s = threadIdx.x % cfg.strips;
-    const int q = threadIdx.x / cfg.strips;
-    int pl = q % cfg.P, seg = q / cfg.P;
+    int pl = threadIdx.x / cfg.strips;
     const int j = j0 + 4 * s;
-    const bool valid = (seg < cfg.nseg) && (p0 + pl < planes) && (j < W);
-    if (seg >= cfg.nseg) { pl = 0; seg = 0; }      // idle lanes read a valid part of the tile, stores off
-    const long p = p0 + pl;
-    const int i0 = it0 + seg * cfg.R;
-    const int i1 = min(min(H, it0 + cfg.Th), i0 + cfg.R);
-
-    mbar_wait(&bar, 0);
-
-    const int toff = pl * rows * pitch + HALO + 4 * s;
-    TileRows<T, kRes> sx{xs + toff, rs + toff, pitch, it0 - 1};
-    TileRows<T, false> sd{ds + toff, nullptr, pitch, it0 - 1};
-    T *dst = out + p * (long)H * W + j;
+    const bool valid = (pl < cfg.P) && (p0 + pl < planes) && (j < W);
+    if (pl >= cfg.P) pl = 0;                        // idle lanes shadow plane 0 of the tile, stores off
+    const bool first_col = (j == 0);
     const bool own0 = (j > 0) && (s == 0 || (threadIdx.x & 31) == 0);
-    strip_core<kBwd>(sx, sd, dst, W, i0, i1, cfg.R, valid, j == 0, own0, kU, kG, kB);
+    const int toff = pl * rows * pitch + HALO + 4 * s;
+    T *dst = out + (p0 + pl) * (long)H * W + j;
+
+    float x0[6], x1[6], d0[6], d1[6], m0[9], m1[9];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { d0[c] = 0.f; d1[c] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) m0[c] = 0.f;        // mid row -1 lies outside the 2x grid
+
+    for (int k = 0; k < cfg.nchunks; ++k) {
+        const unsigned char *base = tile_smem + (k & 1) * stage_bytes;
+        const T *xs = reinterpret_cast<const T *>(base);
+        const T *rs = reinterpret_cast<const T *>(base + (kRes ? cfg.tile_bytes : 0));
+        const T *ds = reinterpret_cast<const T *>(base + (kRes ? 2 : 1) * cfg.tile_bytes);
+        TileRows<T, kRes> sx{xs + toff, rs + toff, pitch, k * cfg.R};
+        TileRows<T, false> sd{ds + toff, nullptr, pitch, k * cfg.R};
+        mbar_wait(&full[k & 1], (k >> 1) & 1);
+        if (k == 0) {
+            sx.load(0, x0);
+            if (kBwd) sd.load(0, d0);
+        }
+        const int r0 = k * cfg.R;
+        for (int i = r0; i < r0 + cfg.R; i += 2) {   // R is even: register roles return to x0/m0
+            strip_step<kBwd>(sx, sd, dst, W, i, valid && i < H, first_col, own0, kU, kG, kB, x0, x1, d0, d1, m0, m1);
+            strip_step<kBwd>(sx, sd, dst, W, i + 1, valid && i + 1 < H, first_col, own0, kU, kG, kB, x1, x0, d1, d0, m1, m0);
+        }
+        __syncthreads();                            // stage k & 1 fully consumed
+        if (threadIdx.x == 0 && k + 2 < cfg.nchunks) issue(k + 2);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -525,14 +556,18 @@ bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dt
     return true;
 }
 
-bool n3_fgelu_tma_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype)
+static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *threads, struct TileCfg *cfg);
+
+bool n3_fgelu_tma_supported(long planes, int H, int W, const void *const *ptrs, int nptrs, int dtype,
+                            int n_inputs)
 {
     if (!n3_fgelu_supported(H, W, ptrs, nptrs, dtype)) return false;
-    if (H < 16 || W < 16) return false;                       // tiny planes: direct path
+    if (H < 2 || W < 16) return false;                        // narrow planes: direct path
     if ((W * esize(dtype)) % 16 != 0) return false;           // TMA global strides
     for (int i = 0; i < nptrs - 1; ++i)                       // inputs only (last ptr = output)
         if (ptrs[i] && !aligned_to(ptrs[i], 16)) return false;
-    return true;
+    int threads; TileCfg cfg;
+    return pick_tile(planes, H, W, dtype, n_inputs, &threads, &cfg);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
@@ -598,29 +633,45 @@ static cudaError_t launch_direct(const void *x, const void *res, const void *dy,
     return cudaGetLastError();
 }
 
-static bool pick_tile(int H, int W, int dtype, int ntiles, int *threads, TileCfg *cfg)
+// Shared-memory budget of one CTA's two-stage ring.  ~52 KB leaves room for four CTAs per SM
+// (16 warps); AFR_RING_KB overrides it for tuning runs.
+static size_t ring_budget_bytes()
+{
+    static size_t v = []() -> size_t {
+        const char *e = getenv("AFR_RING_KB");
+        int kb = e ? atoi(e) : 52;
+        if (kb < 8) kb = 8;
+        if (kb > 96) kb = 96;
+        return (size_t)kb * 1024;
+    }();
+    return v;
+}
+
+static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *threads, TileCfg *cfg)
 {
     const size_t es = esize(dtype);
-    for (int th = 256; th >= 64; th /= 2) {
-        TileCfg c;
-        c.Tw = W <= 128 ? W : 128;
-        c.strips = c.Tw / 4;
-        c.R = pick_rows(H);
-        const int q = th / c.strips;
-        if (q < 1) continue;
-        const int nseg_total = (H + c.R - 1) / c.R;
-        c.nseg = nseg_total < q ? nseg_total : q;
-        c.P = q / c.nseg;
-        c.Th = c.nseg * c.R;
-        c.tiles_x = (W + c.Tw - 1) / c.Tw;
-        c.tiles_y = (H + c.Th - 1) / c.Th;
-        size_t bytes = (size_t)(c.Tw + 2 * (16 / es)) * (c.Th + 2) * c.P * es;
-        c.tile_bytes = (int)((bytes + 127) / 128 * 128);
-        if (c.P > 256 || c.Th + 2 > 256) continue;
-        if ((size_t)c.tile_bytes * ntiles <= 48 * 1024 || th == 64) {
-            if ((size_t)c.tile_bytes * ntiles > 200 * 1024) return false;
-            *threads = th; *cfg = c;
-            return true;
+    TileCfg c;
+    c.Tw = W <= 128 ? W : 128;
+    c.strips = c.Tw / 4;
+    c.tiles_x = (W + c.Tw - 1) / c.Tw;
+    int th = 128;
+    while (th > 32 && th > c.strips && (planes * c.tiles_x * c.strips) / th < 2 * 148) th /= 2;   // small problems: more CTAs
+    if (th < c.strips) th = c.strips;
+    if (th > 128) return false;
+    // chunk height 8 rows (4 if the ring of all staged inputs would not fit the budget); if even
+    // that does not fit, stage fewer planes per CTA; 2-row chunks are the last resort
+    for (int min_r = 4; min_r >= 2; min_r /= 2) {
+        for (int t = th; t >= c.strips && t >= 32; t /= 2) {      // whole warps only (full-mask shuffles)
+            c.P = t / c.strips;
+            for (c.R = 8; c.R >= min_r; c.R /= 2) {
+                const size_t bytes = (size_t)(c.Tw + 2 * (16 / es)) * (c.R + 1) * c.P * es;
+                c.tile_bytes = (int)((bytes + 127) / 128 * 128);
+                if ((size_t)c.tile_bytes * nin * 2 <= ring_budget_bytes()) {
+                    c.nchunks = (H + c.R - 1) / c.R;
+                    *threads = t; *cfg = c;
+                    return true;
+                }
+            }
         }
     }
     return false;
@@ -631,30 +682,30 @@ static cudaError_t launch_tma(const void *x, const void *res, const void *dy, vo
                               long planes, int H, int W, int dtype, const Taps3 &kU,
                               const Taps3 &kG, const Taps3 &kB, cudaStream_t s)
 {
-    const int ntiles = 1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0);
+    const int nin = 1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0);
     int threads; TileCfg cfg;
-    if (!pick_tile(H, W, dtype, ntiles, &threads, &cfg)) { set_detail("no tile configuration"); return cudaErrorInvalidConfiguration; }
+    if (!pick_tile(planes, H, W, dtype, nin, &threads, &cfg)) { set_detail("no tile configuration"); return cudaErrorInvalidConfiguration; }
     CUtensorMap mx, mres, mdy;
-    const int bw = cfg.Tw + 2 * Halo<T>::value, bh = cfg.Th + 2;
+    const int bw = cfg.Tw + 2 * Halo<T>::value, bh = cfg.R + 1;
     if (!make_plane_map(&mx, x, planes, H, W, dtype, bw, bh, cfg.P)) return cudaErrorInvalidValue;
     mres = mx; mdy = mx;
     if (kRes && !make_plane_map(&mres, res, planes, H, W, dtype, bw, bh, cfg.P)) return cudaErrorInvalidValue;
     if (kBwd && !make_plane_map(&mdy, dy, planes, H, W, dtype, bw, bh, cfg.P)) return cudaErrorInvalidValue;
     const long pgroups = (planes + cfg.P - 1) / cfg.P;
-    const long grid = pgroups * cfg.tiles_x * cfg.tiles_y;
+    const long grid = pgroups * cfg.tiles_x;
     if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
-    const size_t smem = (size_t)cfg.tile_bytes * ntiles;
+    const size_t smem = (size_t)cfg.tile_bytes * nin * 2;
     auto kern = fgelu3_tma_kernel<T, kBwd, kRes>;
     static bool attr_set = false;     // per instantiation
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) { set_detail("cudaFuncSetAttribute(max dynamic smem) failed"); return e; }
         attr_set = true;
     }
     kern<<<(unsigned)grid, threads, smem, s>>>(mx, mres, mdy, (T *)out, planes, H, W, cfg, kU, kG, kB);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
-        set_detail("launch grid=%ld block=%d smem=%zu tile Tw=%d Th=%d P=%d", grid, threads, smem, cfg.Tw, cfg.Th, cfg.P);
+        set_detail("launch grid=%ld block=%d smem=%zu tile Tw=%d R=%d P=%d", grid, threads, smem, cfg.Tw, cfg.R, cfg.P);
     return e;
 }
 

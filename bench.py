@@ -146,7 +146,15 @@ def timed_loop(fn, steps, warmup, ws, per_step_events=False):
 
 
 # ---- reference arm: the CPU path on the host cores ----------------------------------------
+def _all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core it may run on."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
 def cpu_reference(sample_b, min_seconds=10.0, max_reps=50):
+    _all_host_threads()
     from oracle import oracle as o
     o.build()
     k = o.lowpass_taps(np.pi / 2, 3, 2.0)
@@ -168,6 +176,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    _all_host_threads()
     from oracle import oracle as o
     o.build()
     k = o.lowpass_taps(np.pi / 2, 3, 2.0)
@@ -182,14 +191,14 @@ def run_reference(args):
     dt = time.perf_counter() - t
     val = args.steps * 2 * x.size * 4 / dt / 1e9
     sample = f"each step = filtered_gelu fwd fp32 on [{sb},{C},{H},{W}] (1/{WORKLOAD['B'] // sb} of the GPU batch)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "filtered_gelu_fwd fp32 [256,128,64,64] N=3 beta=2 omega=pi/2", "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": o.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 # ---- sweep over the other ops / shapes / dtypes (reported, not the headline) ------------------
@@ -269,7 +278,27 @@ def ddpm_v3(afr, ws, rank, global_batch, steps, warmup):
             "afr_launches_per_step": int(launches)}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner to fd 1)
+    get stderr instead; emit() writes to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    claim_stdout()
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -370,7 +399,7 @@ def main():
         except Exception as e:
             out["ddpm_v3"] = {"error": repr(e)[:300]}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if ws > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
