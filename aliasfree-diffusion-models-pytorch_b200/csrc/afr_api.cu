@@ -258,6 +258,8 @@ static int fused_common(const void *x, const void *residual, const void *dy, voi
         const bool use_tma = (path == AFR_PATH_TMA) || (path == AFR_PATH_AUTO && tma_ok);
         Taps3 kU, kG, kB;
         set_taps3(kU, taps_up, false);
+        if (bwd)                       // the adjoint kernels evaluate gelu' in w = kappa * u
+            for (int i = 0; i < 9; ++i) kU.k[i / 3][i % 3] *= AFR_KAPPA;
         set_taps3(kG, taps_down, true);
         set_taps3(kB, bwd ? taps_up : taps_down, bwd);
         return cuda_status(n3_fgelu(x, residual, dy, out, planes, H, W, kU, kG, kB, bwd, dtype, use_tma, s,

@@ -151,21 +151,20 @@ __device__ __forceinline__ float gelu_erf(float x)
     return fmaf(-t, ex2_approx(p), relu_nan(x));
 }
 
-// two GELUs, in place, sharing one FFMA2 Horner chain
+// two GELUs, in place, sharing one FFMA2 Horner chain.  The chain runs in s = -|x| (odd
+// coefficients sign-flipped) so that the final  relu(x) + s * 2^P  is one more packed FMA.
 __device__ __forceinline__ void gelu_erf_x2(float &a, float &b)
 {
-    const float ta = fabsf(a), tb = fabsf(b);
-    const f32x2 t = pack2(ta, tb);
-    f32x2 p = splat2(AFR_P5);
-    p = fma2(p, t, splat2(AFR_P4));
-    p = fma2(p, t, splat2(AFR_P3));
-    p = fma2(p, t, splat2(AFR_P2));
-    p = fma2(p, t, splat2(AFR_P1));
-    p = fma2(p, t, splat2(AFR_P0));
+    const f32x2 sv = pack2(-fabsf(a), -fabsf(b));
+    f32x2 p = splat2(-AFR_P5);
+    p = fma2(p, sv, splat2(AFR_P4));
+    p = fma2(p, sv, splat2(-AFR_P3));
+    p = fma2(p, sv, splat2(AFR_P2));
+    p = fma2(p, sv, splat2(-AFR_P1));
+    p = fma2(p, sv, splat2(AFR_P0));
     float pa, pb;
     unpack2(p, pa, pb);
-    a = fmaf(-ta, ex2_approx(pa), relu_nan(a));
-    b = fmaf(-tb, ex2_approx(pb), relu_nan(b));
+    unpack2(fma2(sv, pack2(ex2_approx(pa), ex2_approx(pb)), pack2(relu_nan(a), relu_nan(b))), a, b);
 }
 
 #define AFR_GELU_T 5.5f
@@ -197,26 +196,78 @@ __device__ __forceinline__ float gelu_erf_grad(float x)
     return x < 0.f ? m : 1.0f - m;
 }
 
-// (ga, gb) <- (gelu'(a) * ga, gelu'(b) * gb)
-__device__ __forceinline__ void gelu_erf_grad_mul_x2(float a, float b, float &ga, float &gb)
+// ---- derivative in the kappa-scaled variable (N == 3 adjoint kernels) -------------------
+// The adjoint kernels receive the up-filter taps pre-multiplied by kappa = sqrt(log2(e)/2), so
+// they hold w = kappa*u and exp(-u^2/2) = 2^(-w^2) needs no scaling multiply; S is re-expressed
+// in v = min(|w|, kappa*5.5).  gelu'(u) = 1/2 + copysign(1/2 - m, u),  m = 2^(-v^2) * S~(v)
+// (the AFR_W* coefficients below are those of -S~ so that 1/2 - m is a single FMA)
+// (1/2 - m > 0 for all v, so the sign transfer is exact).  Packed f32x2 arithmetic throughout.
+#define AFR_KAPPA 0.8493218003f
+#define AFR_VT 4.6712699f
+#define AFR_W8 -1.400882242e-04f
+#define AFR_W7 1.931609655e-03f
+#define AFR_W6 -1.172771243e-02f
+#define AFR_W5 4.260943937e-02f
+#define AFR_W4 -1.079232386e-01f
+#define AFR_W3 2.121540929e-01f
+#define AFR_W2 -3.455765616e-01f
+#define AFR_W1 9.393592619e-01f
+#define AFR_W0 -4.999990023e-01f
+
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
 {
-    const float ta = fminf(fabsf(a), AFR_GELU_T), tb = fminf(fabsf(b), AFR_GELU_T);
-    const float ea = ex2_approx(ta * ta * AFR_NHALF_LOG2E), eb = ex2_approx(tb * tb * AFR_NHALF_LOG2E);
-    const f32x2 t = pack2(ta, tb);
-    f32x2 s = splat2(AFR_S8);
-    s = fma2(s, t, splat2(AFR_S7));
-    s = fma2(s, t, splat2(AFR_S6));
-    s = fma2(s, t, splat2(AFR_S5));
-    s = fma2(s, t, splat2(AFR_S4));
-    s = fma2(s, t, splat2(AFR_S3));
-    s = fma2(s, t, splat2(AFR_S2));
-    s = fma2(s, t, splat2(AFR_S1));
-    s = fma2(s, t, splat2(AFR_S0));
-    float sa, sb;
-    unpack2(s, sa, sb);
-    const float ma = ea * sa, mb = eb * sb;
-    ga *= (a < 0.f ? ma : 1.0f - ma);
-    gb *= (b < 0.f ? mb : 1.0f - mb);
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float copysign_bits(float mag_nonneg, float sgn)
+{
+    return __uint_as_float(__float_as_uint(mag_nonneg) | (__float_as_uint(sgn) & 0x80000000u));
+}
+
+// (ga, gb) <- (gelu'(wa/kappa) * ga, gelu'(wb/kappa) * gb)
+__device__ __forceinline__ void gelu_grad_scaled_mul_x2(float wa, float wb, float &ga, float &gb)
+{
+    const float va = fminf(fabsf(wa), AFR_VT), vb = fminf(fabsf(wb), AFR_VT);
+    const f32x2 v = pack2(va, vb);
+    float qa, qb;
+    unpack2(mul2(v, v), qa, qb);
+    const f32x2 e = pack2(ex2_approx(-qa), ex2_approx(-qb));
+    f32x2 s = splat2(AFR_W8);
+    s = fma2(s, v, splat2(AFR_W7));
+    s = fma2(s, v, splat2(AFR_W6));
+    s = fma2(s, v, splat2(AFR_W5));
+    s = fma2(s, v, splat2(AFR_W4));
+    s = fma2(s, v, splat2(AFR_W3));
+    s = fma2(s, v, splat2(AFR_W2));
+    s = fma2(s, v, splat2(AFR_W1));
+    s = fma2(s, v, splat2(AFR_W0));
+    float ha, hb;
+    unpack2(fma2(e, s, splat2(0.5f)), ha, hb);                          // 1/2 - m   (s = -S~)
+    const f32x2 r = add2(pack2(copysign_bits(ha, wa), copysign_bits(hb, wb)), splat2(0.5f));
+    unpack2(mul2(pack2(ga, gb), r), ga, gb);
+}
+
+__device__ __forceinline__ float gelu_grad_scaled(float w)
+{
+    const float v = fminf(fabsf(w), AFR_VT);
+    const float e = ex2_approx(-v * v);
+    float s = AFR_W8;
+    s = fmaf(s, v, AFR_W7);
+    s = fmaf(s, v, AFR_W6);
+    s = fmaf(s, v, AFR_W5);
+    s = fmaf(s, v, AFR_W4);
+    s = fmaf(s, v, AFR_W3);
+    s = fmaf(s, v, AFR_W2);
+    s = fmaf(s, v, AFR_W1);
+    s = fmaf(s, v, AFR_W0);
+    return 0.5f + copysign_bits(fmaf(e, s, 0.5f), w);
 }
 
 }  // namespace afr

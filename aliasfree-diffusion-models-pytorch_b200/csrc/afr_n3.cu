@@ -11,7 +11,8 @@
 //
 // Forward:  mid = gelu(up(x; kU)),                      out = down(mid; kB), kB = k_down
 // Adjoint:  mid = gelu'(up(x; kU)) * up(dy; kG),        out = down(mid; kB),
-//           kG = flip(k_down), kB = flip(k_up)          (pads are 1/1 for N == 3)
+//           kG = flip(k_down), kB = flip(k_up)          (pads are 1/1 for N == 3);
+//           kU arrives pre-scaled by kappa (afr_common.cuh) so that the kernel holds kappa*u
 // mid is forced to zero outside [0,2H) x [0,2W): only column 2j-1 at j == 0 and row
 // 2i-1 at i == 0 can fall outside, which is what `first_col` / the i0 == 0 start handle.
 //
@@ -70,7 +71,7 @@ __device__ __forceinline__ void act_cols_1_8(float (&u)[9], float (&g)[9])
 {
 #pragma unroll
     for (int c = 1; c < 9; c += 2) {
-        if (kBwd) gelu_erf_grad_mul_x2(u[c], u[c + 1], g[c], g[c + 1]);
+        if (kBwd) gelu_grad_scaled_mul_x2(u[c], u[c + 1], g[c], g[c + 1]);
         else gelu_erf_x2(u[c], u[c + 1]);
     }
 }
@@ -78,14 +79,14 @@ __device__ __forceinline__ void act_cols_1_8(float (&u)[9], float (&g)[9])
 template <bool kBwd>
 __device__ __forceinline__ void act_col0_single(float (&u)[9], float (&g)[9])
 {
-    if (kBwd) g[0] *= gelu_erf_grad(u[0]);
+    if (kBwd) g[0] *= gelu_grad_scaled(u[0]);
     else u[0] = gelu_erf(u[0]);
 }
 
 template <bool kBwd>
 __device__ __forceinline__ void act_col0_pair(float (&ue)[9], float (&uo)[9], float (&ge)[9], float (&go)[9])
 {
-    if (kBwd) gelu_erf_grad_mul_x2(ue[0], uo[0], ge[0], go[0]);
+    if (kBwd) gelu_grad_scaled_mul_x2(ue[0], uo[0], ge[0], go[0]);
     else gelu_erf_x2(ue[0], uo[0]);
 }
 
@@ -271,13 +272,15 @@ fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T
                      const __grid_constant__ Taps3 kU, const __grid_constant__ Taps3 kG,
                      const __grid_constant__ Taps3 kB)
 {
-    long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    const long per_plane = (long)strips * nseg;
-    const bool valid = idx < planes * per_plane;
+    // 32-bit index arithmetic (the launcher guarantees planes * strips * nseg < 2^31)
+    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned per_plane = (unsigned)(strips * nseg);
+    const bool valid = idx < (unsigned)planes * per_plane;
     if (!valid) idx = 0;                           // idle lanes shadow thread 0, stores off
-    const int s = (int)(idx % strips);
-    const int seg = (int)((idx / strips) % nseg);
-    const long p = idx / per_plane;
+    const unsigned pu = idx / per_plane, rem = idx - pu * per_plane;
+    const int seg = (int)(rem / (unsigned)strips);
+    const int s = (int)(rem - (unsigned)seg * (unsigned)strips);
+    const long p = pu;
     const int j = 4 * s, i0 = seg * R, i1 = min(H, i0 + R);
     const long base = p * (long)H * W + j;
     GlobalRows<T, kRes> sx{x + base, kRes ? res + base : nullptr, H, W, j};
@@ -558,11 +561,17 @@ bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dt
 
 static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *threads, struct TileCfg *cfg);
 
+static int tma_min_width()
+{
+    static int v = []() { const char *e = getenv("AFR_TMA_MIN_W"); int w = e ? atoi(e) : 8; return w < 4 ? 4 : w; }();
+    return v;
+}
+
 bool n3_fgelu_tma_supported(long planes, int H, int W, const void *const *ptrs, int nptrs, int dtype,
                             int n_inputs)
 {
     if (!n3_fgelu_supported(H, W, ptrs, nptrs, dtype)) return false;
-    if (H < 2 || W < 16) return false;                        // narrow planes: direct path
+    if (H < 2 || W < tma_min_width()) return false;           // narrow planes: direct path
     if ((W * esize(dtype)) % 16 != 0) return false;           // TMA global strides
     for (int i = 0; i < nptrs - 1; ++i)                       // inputs only (last ptr = output)
         if (ptrs[i] && !aligned_to(ptrs[i], 16)) return false;
@@ -627,7 +636,7 @@ static cudaError_t launch_direct(const void *x, const void *res, const void *dy,
     const long total = planes * (long)strips * nseg;
     const int block = 128;
     const long grid = (total + block - 1) / block;
-    if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    if (total >= 0x7fffffffL) { set_detail("tensor too large for the direct kernel's 32-bit indexing"); return cudaErrorInvalidConfiguration; }
     fgelu3_direct_kernel<T, kBwd, kRes><<<(unsigned)grid, block, 0, s>>>(
         (const T *)x, (const T *)res, (const T *)dy, (T *)out, planes, H, W, strips, nseg, R, kU, kG, kB);
     return cudaGetLastError();
@@ -654,8 +663,10 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
     c.Tw = W <= 128 ? W : 128;
     c.strips = c.Tw / 4;
     c.tiles_x = (W + c.Tw - 1) / c.Tw;
+    // 128-thread CTAs unless that leaves fewer than ~6 CTAs per SM: long-lived streaming CTAs
+    // need a few waves to balance, so small batches of large planes use smaller CTAs
     int th = 128;
-    while (th > 32 && th > c.strips && (planes * c.tiles_x * c.strips) / th < 2 * 148) th /= 2;   // small problems: more CTAs
+    while (th > 32 && th > c.strips && (planes * c.tiles_x * c.strips) / th < 6 * 148) th /= 2;
     if (th < c.strips) th = c.strips;
     if (th > 128) return false;
     // chunk height 8 rows (4 if the ring of all staged inputs would not fit the budget); if even
