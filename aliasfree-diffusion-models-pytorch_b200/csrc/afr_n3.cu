@@ -341,11 +341,15 @@ template <typename T> struct Halo { static constexpr int value = 16 / (int)sizeo
 
 // Row-streaming tile configuration: a CTA owns P planes x one column tile of Tw outputs and
 // walks down ALL rows of those planes in chunks of R rows; chunk k is the box
-// [Tw + 2*halo, R + 1 rows (kR .. kR+R), P planes] and lands in stage k & 1.
+// [Tw + 2*halo, R + 1 rows (kR .. kR+R), P planes] and lands in stage k & 1.  Small batches of
+// large planes are additionally split into `nsegs` row segments (blockIdx.y) to fill the GPU; a
+// segment that does not start at row 0 begins one row early with its store switched off, which
+// builds the carried mid row.
 struct TileCfg {
     int Tw, R, P;              // tile width (outputs), rows per chunk, planes per CTA
     int strips;                // Tw / 4 : threads per plane row
-    int tiles_x, nchunks;      // column tiles per plane, row chunks per plane
+    int tiles_x;               // column tiles per plane
+    int nsegs, Hs;             // row segments per plane (blockIdx.y) and their height
     int tile_bytes;            // bytes of one staged box, rounded up to 128
 };
 
@@ -372,13 +376,19 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     const int stage_bytes = NIN * cfg.tile_bytes;
     const uint32_t box_bytes = (uint32_t)(pitch * rows * cfg.P * sizeof(T));
 
+    const int seg_lo = (int)blockIdx.y * cfg.Hs;                 // first / one-past-last output row
+    const int seg_hi = min(H, seg_lo + cfg.Hs);
+    const int istart = seg_lo > 0 ? seg_lo - 1 : 0;              // first step (a dry one if seg_lo > 0)
+    const int nchunks = (seg_hi - istart + cfg.R - 1) / cfg.R;
+
     auto issue = [&](int k) {          // one thread: arm the stage's barrier, launch its boxes
         unsigned char *base = tile_smem + (k & 1) * stage_bytes;
         uint64_t *bar = &full[k & 1];
+        const int row = istart + k * cfg.R;
         mbar_expect_tx(bar, box_bytes * NIN);
-        tma_load_3d(base, &mx, bar, j0 - HALO, k * cfg.R, (int)p0);
-        if (kRes) tma_load_3d(base + cfg.tile_bytes, &mres, bar, j0 - HALO, k * cfg.R, (int)p0);
-        if (kBwd) tma_load_3d(base + (kRes ? 2 : 1) * cfg.tile_bytes, &mdy, bar, j0 - HALO, k * cfg.R, (int)p0);
+        tma_load_3d(base, &mx, bar, j0 - HALO, row, (int)p0);
+        if (kRes) tma_load_3d(base + cfg.tile_bytes, &mres, bar, j0 - HALO, row, (int)p0);
+        if (kBwd) tma_load_3d(base + (kRes ? 2 : 1) * cfg.tile_bytes, &mdy, bar, j0 - HALO, row, (int)p0);
     };
 
     if (threadIdx.x == 0) {
@@ -389,7 +399,7 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     __syncthreads();
     if (threadIdx.x == 0) {
         issue(0);
-        if (cfg.nchunks > 1) issue(1);
+        if (nchunks > 1) issue(1);
     }
 
     const int s = threadIdx.x % cfg.strips;
@@ -408,25 +418,27 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
 #pragma unroll
     for (int c = 0; c < 9; ++c) m0[c] = 0.f;        // mid row -1 lies outside the 2x grid
 
-    for (int k = 0; k < cfg.nchunks; ++k) {
+    for (int k = 0; k < nchunks; ++k) {
         const unsigned char *base = tile_smem + (k & 1) * stage_bytes;
         const T *xs = reinterpret_cast<const T *>(base);
         const T *rs = reinterpret_cast<const T *>(base + (kRes ? cfg.tile_bytes : 0));
         const T *ds = reinterpret_cast<const T *>(base + (kRes ? 2 : 1) * cfg.tile_bytes);
-        TileRows<T, kRes> sx{xs + toff, rs + toff, pitch, k * cfg.R};
-        TileRows<T, false> sd{ds + toff, nullptr, pitch, k * cfg.R};
+        const int r0 = istart + k * cfg.R;
+        TileRows<T, kRes> sx{xs + toff, rs + toff, pitch, r0};
+        TileRows<T, false> sd{ds + toff, nullptr, pitch, r0};
         mbar_wait(&full[k & 1], (k >> 1) & 1);
         if (k == 0) {
-            sx.load(0, x0);
-            if (kBwd) sd.load(0, d0);
+            sx.load(r0, x0);
+            if (kBwd) sd.load(r0, d0);
         }
-        const int r0 = k * cfg.R;
         for (int i = r0; i < r0 + cfg.R; i += 2) {   // R is even: register roles return to x0/m0
-            strip_step<kBwd>(sx, sd, dst, W, i, valid && i < H, first_col, own0, kU, kG, kB, x0, x1, d0, d1, m0, m1);
-            strip_step<kBwd>(sx, sd, dst, W, i + 1, valid && i + 1 < H, first_col, own0, kU, kG, kB, x1, x0, d1, d0, m1, m0);
+            strip_step<kBwd>(sx, sd, dst, W, i, valid && i >= seg_lo && i < seg_hi, first_col, own0, kU, kG, kB,
+                             x0, x1, d0, d1, m0, m1);
+            strip_step<kBwd>(sx, sd, dst, W, i + 1, valid && i + 1 >= seg_lo && i + 1 < seg_hi, first_col, own0, kU,
+                             kG, kB, x1, x0, d1, d0, m1, m0);
         }
         __syncthreads();                            // stage k & 1 fully consumed
-        if (threadIdx.x == 0 && k + 2 < cfg.nchunks) issue(k + 2);
+        if (threadIdx.x == 0 && k + 2 < nchunks) issue(k + 2);
     }
 }
 
@@ -678,7 +690,13 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
                 const size_t bytes = (size_t)(c.Tw + 2 * (16 / es)) * (c.R + 1) * c.P * es;
                 c.tile_bytes = (int)((bytes + 127) / 128 * 128);
                 if ((size_t)c.tile_bytes * nin * 2 <= ring_budget_bytes()) {
-                    c.nchunks = (H + c.R - 1) / c.R;
+                    // row segments: only when whole-plane streaming leaves the GPU under-filled
+                    // (< ~20 warps per SM); each extra segment costs one dry step
+                    const long warps = (planes * c.tiles_x * c.strips + 31) / 32;
+                    c.nsegs = 1;
+                    while (warps * c.nsegs < 20L * 148 && H / (c.nsegs * 2) >= 2 * c.R && c.nsegs < 16) c.nsegs *= 2;
+                    c.Hs = ((H + c.nsegs - 1) / c.nsegs + c.R - 1) / c.R * c.R;
+                    c.nsegs = (H + c.Hs - 1) / c.Hs;
                     *threads = t; *cfg = c;
                     return true;
                 }
@@ -705,6 +723,7 @@ static cudaError_t launch_tma(const void *x, const void *res, const void *dy, vo
     const long pgroups = (planes + cfg.P - 1) / cfg.P;
     const long grid = pgroups * cfg.tiles_x;
     if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    const dim3 grid3((unsigned)grid, (unsigned)cfg.nsegs);
     const size_t smem = (size_t)cfg.tile_bytes * nin * 2;
     auto kern = fgelu3_tma_kernel<T, kBwd, kRes>;
     static bool attr_set = false;     // per instantiation
@@ -713,7 +732,7 @@ static cudaError_t launch_tma(const void *x, const void *res, const void *dy, vo
         if (e != cudaSuccess) { set_detail("cudaFuncSetAttribute(max dynamic smem) failed"); return e; }
         attr_set = true;
     }
-    kern<<<(unsigned)grid, threads, smem, s>>>(mx, mres, mdy, (T *)out, planes, H, W, cfg, kU, kG, kB);
+    kern<<<grid3, threads, smem, s>>>(mx, mres, mdy, (T *)out, planes, H, W, cfg, kU, kG, kB);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         set_detail("launch grid=%ld block=%d smem=%zu tile Tw=%d R=%d P=%d", grid, threads, smem, cfg.Tw, cfg.R, cfg.P);
