@@ -320,7 +320,20 @@ int afr_ddpm_update(void *x, const void *eps, const void *noise, int64_t n, floa
     begin_call();
     g_last_kernel = "ddpm_update_kernel";
     return cuda_status(ddpm_update((float *)x, (const float *)eps, (const float *)noise, (long)n, ca, cb,
-                                   cc, (cudaStream_t)stream),
+                                   cc, nullptr, nullptr, (cudaStream_t)stream),
+                       "ddpm_update_kernel");
+}
+
+int afr_ddpm_update_table(void *x, const void *eps, const void *noise, int64_t n, const float *table_dev,
+                          const int *step_dev, void *stream)
+{
+    if (n < 0) return fail(AFR_ERR_BAD_SHAPE, "n < 0");
+    if (n == 0) return AFR_OK;
+    if (!x || !eps || !table_dev || !step_dev) return fail(AFR_ERR_NULL_POINTER, "NULL pointer");
+    begin_call();
+    g_last_kernel = "ddpm_update_kernel";
+    return cuda_status(ddpm_update((float *)x, (const float *)eps, (const float *)noise, (long)n, 0.f, 0.f,
+                                   0.f, table_dev, step_dev, (cudaStream_t)stream),
                        "ddpm_update_kernel");
 }
 

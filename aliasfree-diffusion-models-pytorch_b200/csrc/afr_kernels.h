@@ -39,6 +39,6 @@ cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, c
 cudaError_t rotate_periodic_cubic(const float *x, float *y, long planes, int H, int W,
                                   double degrees, cudaStream_t s);
 cudaError_t ddpm_update(float *x, const float *eps, const float *noise, long n, float ca,
-                        float cb, float cc, cudaStream_t s);
+                        float cb, float cc, const float *table_dev, const int *step_dev, cudaStream_t s);
 
 }  // namespace afr

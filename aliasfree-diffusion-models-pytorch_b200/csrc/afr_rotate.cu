@@ -110,8 +110,13 @@ cudaError_t rotate_periodic_cubic(const float *x, float *y, long planes, int H, 
 // x <- ca * (x - cb * eps) + cc * noise      (modules/ddpm_models.py:374)
 __global__ void __launch_bounds__(256)
 ddpm_update_kernel(float *__restrict__ x, const float *__restrict__ eps,
-                   const float *__restrict__ noise, long n4, long n, float ca, float cb, float cc)
+                   const float *__restrict__ noise, long n4, long n, float ca, float cb, float cc,
+                   const float *__restrict__ table, const int *__restrict__ step)
 {
+    if (table) {                                   // graph-replay flavour: coefficients live on the device
+        const int i = *step;
+        ca = table[3 * i]; cb = table[3 * i + 1]; cc = table[3 * i + 2];
+    }
     const long stride = (long)gridDim.x * blockDim.x;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 a = reinterpret_cast<float4 *>(x)[i];
@@ -132,7 +137,7 @@ ddpm_update_kernel(float *__restrict__ x, const float *__restrict__ eps,
 }
 
 cudaError_t ddpm_update(float *x, const float *eps, const float *noise, long n, float ca, float cb,
-                        float cc, cudaStream_t s)
+                        float cc, const float *table_dev, const int *step_dev, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps) |
@@ -141,7 +146,7 @@ cudaError_t ddpm_update(float *x, const float *eps, const float *noise, long n, 
     long grid = ((vec ? n4 : n) + 255) / 256;
     if (grid < 1) grid = 1;
     if (grid > 148 * 16) grid = 148 * 16;
-    ddpm_update_kernel<<<(unsigned)grid, 256, 0, s>>>(x, eps, noise, n4, n, ca, cb, cc);
+    ddpm_update_kernel<<<(unsigned)grid, 256, 0, s>>>(x, eps, noise, n4, n, ca, cb, cc, table_dev, step_dev);
     return cudaGetLastError();
 }
 

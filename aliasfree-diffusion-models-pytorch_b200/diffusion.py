@@ -78,21 +78,80 @@ class Diffusion:
                 kept.append(x.clone())
         return x, kept
 
+    # -- one reverse step captured in a CUDA graph --------------------------------------------
+    def capture_reverse_step(self, model, x, theta=None):
+        """Capture ONE reverse step acting in place on ``x`` (UNet forward, noise draw, posterior
+        update, optional rotation, timestep decrement) in a CUDA graph.  Returns ``(graph, step)``:
+        ``step`` is the int32 device scalar holding the current timestep (set it to T-1 before the
+        first replay); each ``graph.replay()`` advances x by one step with no host work.  The
+        (ca, cb, cc) coefficients are read on the device from a [T, 3] table.  Noise comes from
+        torch's graph-safe CUDA generator: results match the eager sampler in distribution, not
+        bit for bit."""
+        dev, n, T = x.device, x.shape[0], self.noise_steps
+        cc = list(self._cc)
+        if T > 1:
+            cc[1] = 0.0                                               # no noise on the final step (:372)
+        table = torch.tensor([[a, b, c] for a, b, c in zip(self._ca, self._cb, cc)],
+                             dtype=torch.float32, device=dev).contiguous()
+        step = torch.full((1,), T - 1, dtype=torch.int32, device=dev)
+        t_long = torch.empty(n, dtype=torch.long, device=dev)
+        theta_step = None if theta is None else theta / T
+
+        def body():
+            t_long.copy_(step.expand(n))
+            eps = model(x, t_long).float().contiguous()
+            noise = torch.randn_like(x)
+            ops.ddpm_update_table_(x, eps, noise, table, step)
+            if theta_step is not None:
+                x.copy_(ops.rotate(x, theta_step))
+            step.sub_(1)
+
+        x_keep = x.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():               # warm-up outside capture (lazy inits)
+            for _ in range(2):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        x.copy_(x_keep); step.fill_(T - 1)
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            body()
+        x.copy_(x_keep); step.fill_(T - 1)                            # capture itself executes nothing
+        graph._afr_keepalive = (table, t_long)                        # tensors the graph reads
+        return graph, step
+
+    def _graphed_loop(self, model, n, image_channels, theta, keep, x_init, generator):
+        x = self._initial(n, image_channels, x_init, generator)
+        graph, _ = self.capture_reverse_step(model, x, theta)
+        kept = []
+        for i in reversed(range(1, self.noise_steps)):
+            graph.replay()
+            if keep and i % 100 == 0:
+                kept.append(x.clone())
+        return x, kept
+
     @staticmethod
     def _to_u8(x):
         return (((x.clamp(-1, 1) + 1) / 2) * 255).type(torch.uint8)
 
     def sample(self, model, n, image_channels, theta=None, x_init=None, generator=None,
-               noise_source=None, progress=False, return_float=False):
+               noise_source=None, progress=False, return_float=False, cuda_graph=False):
         """Ancestral sampling, ddpm_models.py:352-386.  Returns ``(x_u8, result_u8)`` like the
         reference (``result`` = snapshots every 100 steps + the final x).  ``noise_source(x)``
         lets a caller inject the per-step noise (tests replay the reference's CPU stream;
-        the sharded sampler slices a full-batch stream)."""
+        the sharded sampler slices a full-batch stream).  ``cuda_graph=True`` captures one reverse
+        step in a CUDA graph and replays it (launch-bound small batches: several times faster)."""
         logging.info(f"Sampling {n} new images....")
         model.eval()
         with torch.no_grad():
-            x, kept = self._loop(model, n, image_channels, theta, True, x_init, generator,
-                                 noise_source, progress)
+            if cuda_graph:
+                if noise_source is not None:
+                    raise ValueError("cuda_graph=True draws its noise inside the graph; noise_source is unsupported")
+                x, kept = self._graphed_loop(model, n, image_channels, theta, True, x_init, generator)
+            else:
+                x, kept = self._loop(model, n, image_channels, theta, True, x_init, generator,
+                                     noise_source, progress)
         model.train()                       # the reference unconditionally does (:379)
         kept.append(x)
         if return_float:

@@ -224,3 +224,18 @@ def ddpm_update_(x, eps, noise, ca, cb, cc):
                                              None if noise is None else noise.data_ptr(),
                                              x.numel(), float(ca), float(cb), float(cc), _stream(x)))
     return x
+
+
+def ddpm_update_table_(x, eps, noise, table, step):
+    """Like ``ddpm_update_`` but (ca, cb, cc) are read on the device from ``table[step]``
+    (``table``: float32 CUDA [T, 3]; ``step``: int32 CUDA scalar tensor) -- graph-capturable."""
+    for t in (x, eps, table) + (() if noise is None else (noise,)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError("afr: ddpm_update_table_ needs contiguous float32 CUDA tensors")
+    if not (step.is_cuda and step.dtype == torch.int32):
+        raise RuntimeError("afr: step must be an int32 CUDA tensor")
+    with torch.cuda.device(x.device):
+        _check(_native.lib().afr_ddpm_update_table(x.data_ptr(), eps.data_ptr(),
+                                                   None if noise is None else noise.data_ptr(),
+                                                   x.numel(), table.data_ptr(), step.data_ptr(), _stream(x)))
+    return x

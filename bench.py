@@ -262,16 +262,27 @@ def ddpm_v3(afr, ws, rank, global_batch, steps, warmup):
     x = torch.randn(n, 3, 32, 32, device="cuda")
     state = {"i": 999}
 
-    def step():
+    def eager_step():
         with torch.no_grad():
             diff._reverse_step(net, x, state["i"], torch.randn_like(x))
         state["i"] -= 1
 
     l0 = afr.launch_count()
-    total_ms, _ = timed_loop(step, steps, warmup, ws)
+    eager_ms, _ = timed_loop(eager_step, steps, warmup, ws)
+    eager_ms /= steps
     launches = (afr.launch_count() - l0) // (steps + warmup)
-    ms = total_ms / steps
-    return {"samples_per_sec": global_batch / (999 * ms / 1e3), "ms_per_reverse_step": ms,
+    ms, mode = eager_ms, "eager"
+    try:                                   # one reverse step captured in a CUDA graph and replayed
+        graph, step_dev = diff.capture_reverse_step(net, x)
+        step_dev.fill_(900)
+        g_ms, _ = timed_loop(graph.replay, steps, warmup, ws)
+        g_ms /= steps
+        if g_ms < ms:
+            ms, mode = g_ms, "cuda_graph"
+    except Exception as e:                 # capture is an optimisation, never a requirement
+        mode = "eager (graph capture failed: %s)" % repr(e)[:120]
+    return {"samples_per_sec": global_batch / (999 * ms / 1e3), "ms_per_reverse_step": ms, "mode": mode,
+            "eager_ms_per_reverse_step": eager_ms,
             "global_batch": global_batch, "per_rank_batch": n, "steps_timed": steps,
             "note": "random-init UNet variant=3 c=3 32x32, fp32 (PyTorch default TF32 conv); "
                     "samples/sec = batch / (999 x measured ms per reverse step); strong scaling over ranks",

@@ -102,8 +102,8 @@ int afr_filtered_gelu_bwd(const void *x, const void *residual, const void *dy, v
 /* Diffusion.rotate_2d_matrix(matrix, degrees)          modules/ddpm_models.py:421-429
  * = scipy.ndimage.rotate(axes=(2,3), reshape=False, order=3, mode='grid-wrap'):
  * periodic cubic B-spline prefilter + 4x4-tap gather, entirely on device.
- * x, y: [B,C,H,W] fp32 (dtype must be AFR_F32), H*W <= 16384. x may equal y only if
- * they do not alias partially (in-place is NOT supported). */
+ * x, y: [B,C,H,W] fp32 (dtype must be AFR_F32), H*W <= 16384; x and y must not alias
+ * (in-place is not supported). */
 int afr_rotate_periodic_cubic(const void *x, void *y, int B, int C, int H, int W,
                               double degrees, int dtype, void *stream);
 
@@ -111,6 +111,13 @@ int afr_rotate_periodic_cubic(const void *x, void *y, int B, int C, int H, int W
  * x <- ca * (x - cb * eps) + cc * noise, elementwise over n floats (fp32). noise may be NULL. */
 int afr_ddpm_update(void *x, const void *eps, const void *noise, int64_t n,
                     float ca, float cb, float cc, void *stream);
+
+/* Same update with the step's coefficients read ON THE DEVICE, so that a whole reverse step can
+ * be captured once in a CUDA graph and replayed for every i:
+ * table is a device array [T][3] of (ca, cb, cc) per timestep, step_dev a device int holding the
+ * current timestep i (1 <= i < T). */
+int afr_ddpm_update_table(void *x, const void *eps, const void *noise, int64_t n,
+                          const float *table_dev, const int *step_dev, void *stream);
 
 #ifdef __cplusplus
 }

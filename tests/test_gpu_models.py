@@ -133,6 +133,24 @@ def test_sharded_sampler_equals_unsharded(afr):
         assert (got.int() - full.int()).abs().max().item() <= 1
 
 
+def test_cuda_graph_sampler_matches_eager(afr):
+    """One reverse step captured in a CUDA graph and replayed == the eager loop (noise zeroed on
+    both sides so the comparison is deterministic), with and without the Config-E rotation."""
+    from unittest import mock
+    net = fill_params_(afr.UNet(c_in=3, c_out=3, image_size=16, f_settings=FS, variant=3)).cuda()
+    diff = afr.Diffusion(noise_steps=8, img_size=16, device="cuda")
+    x0 = torch.randn(3, 3, 16, 16, generator=torch.Generator().manual_seed(3))
+    for theta in (None, 40.0):
+        with mock.patch.object(torch, "randn_like", torch.zeros_like):
+            want, _ = diff.sample(net, 3, 3, theta=theta, x_init=x0, return_float=True)
+            got, kept = diff.sample(net, 3, 3, theta=theta, x_init=x0, return_float=True, cuda_graph=True)
+        assert relmax(host(got), host(want)) <= 1e-4
+        assert kept.shape[0] == 3                     # no i % 100 snapshot in 7 steps, just the final x
+    # and with real noise it runs and stays finite
+    x_u8, res_u8 = diff.sample(net, 3, 3, x_init=x0, cuda_graph=True)
+    assert x_u8.dtype == torch.uint8 and tuple(x_u8.shape) == (3, 3, 16, 16)
+
+
 def test_train_step_runs_and_matches_autograd(afr):
     from aliasfree_b200 import parallel
     torch.manual_seed(0)
