@@ -201,6 +201,39 @@ def run_reference(args):
         "gpu_launches": 0})
 
 
+# ---- the upstream GPU path: the reference's own PyTorch calls, eager, on this B200 ---------------
+def reference_eager_gpu(afr):
+    """What the unmodified reference executes on a GPU (zero-stuff + depthwise F.conv2d + slice +
+    F.gelu, with its per-call filter upload), restated in oracle/torch_restatement.py because the
+    reference checkout is not on the GPU box.  Smaller batch than the headline: the unfused path
+    materialises three 4x-sized tensors.  Reported next to our kernel on the SAME tensor."""
+    from oracle import torch_restatement as tr
+    B, C, H, W = 64, WORKLOAD["C"], WORKLOAD["H"], WORKLOAD["W"]
+    x = torch.randn(B, C, H, W, device="cuda")
+    k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
+    kt = afr.Taps(k)
+    nbytes = 2 * x.numel() * 4
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+
+    def tm(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    with torch.no_grad():
+        ref_ms = tm(lambda: tr.filtered_gelu(x, k, k))
+        ours_ms = tm(lambda: afr.ops._fgelu_fwd(x, None, kt, kt))
+        err = float((tr.filtered_gelu(x, k, k) - afr.ops._fgelu_fwd(x, None, kt, kt)).abs().max())
+    return {"shape": [B, C, H, W], "dtype": "f32", "reference_eager_ms": ref_ms, "reference_eager_GBps": nbytes / ref_ms / 1e6,
+            "ours_ms": ours_ms, "ours_GBps": nbytes / ours_ms / 1e6, "speedup": ref_ms / ours_ms, "max_abs_diff": err,
+            "note": "algorithmic bytes 2*n*4 for both; reference = oracle/torch_restatement.py (the upstream eager op sequence)"}
+
+
 # ---- sweep over the other ops / shapes / dtypes (reported, not the headline) ------------------
 def sweep(afr, quick):
     k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
@@ -398,6 +431,11 @@ def main():
     elif rank == 0:
         out["cpu_baseline"] = None
     if not args.no_sweep and ws == 1:
+        torch.cuda.empty_cache()
+        try:
+            out["reference_eager_gpu"] = reference_eager_gpu(afr)
+        except Exception as e:
+            out["reference_eager_gpu"] = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
         try:
             out["sweep"] = sweep(afr, quick=not args.full_sweep)

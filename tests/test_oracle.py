@@ -93,3 +93,15 @@ def test_empty_and_shapes(oracle):
     assert oracle.up2x(np.zeros((0, 4, 4), np.float32), k).shape == (0, 8, 8)
     assert oracle.down2x(np.zeros((2, 7, 9), np.float32), k).shape == (2, 4, 5)
     assert oracle.filtered_gelu(np.zeros((1, 1, 1), np.float32), k, k).shape == (1, 1, 1)
+
+
+def test_torch_restatement_matches_reference():
+    """oracle/torch_restatement.py (used by bench.py as the eager-GPU baseline) on CPU vs the goldens."""
+    import torch
+    from oracle import torch_restatement as tr
+    g = golden("resample.npz")
+    for name in _cases():
+        x = torch.from_numpy(g[f"{name}.x"]); ku = torch.from_numpy(g[f"{name}.ku"]); kd = torch.from_numpy(g[f"{name}.kd"])
+        assert relmax(tr.custom_upsample(x, ku).numpy(), g[f"{name}.up"]) <= 1e-6
+        assert relmax(tr.custom_downsample(x, kd).contiguous().numpy(), g[f"{name}.down"]) <= 1e-6
+        assert relmax(tr.filtered_gelu(x, ku, kd).contiguous().numpy(), g[f"{name}.fused"]) <= 1e-6
