@@ -13,6 +13,7 @@ from .unet import UNet
 from .diffusion import Diffusion
 from .patch import patch, unpatch
 from . import parallel
+from .tasks import rotation_results, shift_results
 
 build = _native.build
 set_path = _native.set_path
@@ -22,5 +23,5 @@ launch_count = _native.launch_count
 __all__ = ["circularLowpassKernel", "taps_from_settings", "Taps", "custom_upsample",
            "custom_downsample", "up2x", "down2x", "filtered_gelu", "rotate", "ddpm_update_",
            "DoubleConv", "DoubleConv_F", "Down", "Down_F", "Down_FF", "Down_FFF", "Up", "Up_F",
-           "Up_FF", "Up_FFF", "SelfAttention", "UNet", "Diffusion", "patch", "unpatch", "parallel",
+           "Up_FF", "Up_FFF", "SelfAttention", "UNet", "Diffusion", "patch", "unpatch", "parallel", "rotation_results", "shift_results",
            "build", "set_path", "last_kernel", "launch_count"]

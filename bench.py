@@ -341,6 +341,56 @@ def emit(obj):
     _JSON_OUT.flush()
 
 
+# ---- Config-D training step (BASELINE configs[1]) ---------------------------------------------------
+def train_v3(afr, ws, rank, global_batch, steps, warmup):
+    """Inner step of the reference train() (modules/ddpm_utils.py:498-509) on synthetic CIFAR-shaped
+    images: H2D of the rank's batch from pinned memory, timesteps, q-sample, forward, MSE, backward,
+    ONE flat-gradient all-reduce (N > 1), AdamW, loss read-back."""
+    from aliasfree_b200 import parallel
+    torch.manual_seed(0)
+    net = afr.UNet(c_in=3, c_out=3, image_size=32, f_settings=FS, variant=3).cuda().train()
+    diff = afr.Diffusion(noise_steps=1000, img_size=32, device="cuda")
+    opt = torch.optim.AdamW(net.parameters(), lr=3e-4)
+    ddp = parallel.FlatGradAllReduce(net)
+    lo, hi = parallel.shard_bounds(global_batch, rank, ws)
+    host = (torch.rand(hi - lo, 3, 32, 32) * 2 - 1).pin_memory()
+    dev = torch.empty_like(host, device="cuda")
+    losses = []
+
+    def step():
+        dev.copy_(host, non_blocking=True)
+        loss = parallel.train_step(net, diff, opt, dev, ddp=ddp)
+        losses.append(loss.detach())
+
+    l0 = afr.launch_count()
+    total_ms, _ = timed_loop(step, steps, warmup, ws)
+    launches = (afr.launch_count() - l0) // (steps + warmup)
+    ms = total_ms / steps
+    return {"images_per_sec": global_batch / (ms / 1e3), "ms_per_step": ms, "global_batch": global_batch,
+            "per_rank_batch": hi - lo, "steps_timed": steps, "final_loss": float(losses[-1].item()),
+            "afr_launches_per_step": int(launches), "params": sum(p.numel() for p in net.parameters()),
+            "note": "variant=3 c=3 32x32 fp32, AdamW lr 3e-4, one flat-gradient NCCL all-reduce per step when N > 1"}
+
+
+# ---- Config-E rotation sweep (BASELINE configs[3]) -----------------------------------------------------
+def config_e(afr, steps_per_frame=100):
+    """One frame of the rotation sweep (n=4, 3x32x32, theta=45) on a shortened schedule, eager vs the
+    captured CUDA graph; the per-step rotation runs on the device (the reference round-trips through
+    scipy on the host every step)."""
+    torch.manual_seed(0)
+    net = afr.UNet(c_in=3, c_out=3, image_size=32, f_settings=FS, variant=3).cuda().eval()
+    diff = afr.Diffusion(noise_steps=steps_per_frame + 1, img_size=32, device="cuda")
+    out = {}
+    for mode, flag in (("eager", False), ("cuda_graph", True)):
+        diff.sample(net, 4, 3, theta=45.0, cuda_graph=flag)          # warm-up (and graph capture cost excluded below)
+        torch.cuda.synchronize(); t = time.perf_counter()
+        diff.sample(net, 4, 3, theta=45.0, cuda_graph=flag)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t
+        out[mode + "_ms_per_step"] = 1e3 * dt / steps_per_frame
+    out["note"] = f"n=4, theta=45, {steps_per_frame} reverse steps incl. on-device periodic-cubic rotation; wall clock incl. capture for the graph mode"
+    return out
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -353,6 +403,8 @@ def main():
     ap.add_argument("--no-ddpm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ddpm-batch", type=int, default=4096)
+    ap.add_argument("--train-batch", type=int, default=256)
+    ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--path", default="auto", choices=["auto", "direct", "tma", "generic"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -447,6 +499,17 @@ def main():
             out["ddpm_v3"] = ddpm_v3(afr, ws, rank, args.ddpm_batch, steps=min(args.steps, 5), warmup=3)
         except Exception as e:
             out["ddpm_v3"] = {"error": repr(e)[:300]}
+    if not args.no_train:
+        torch.cuda.empty_cache()
+        try:
+            out["train_v3"] = train_v3(afr, ws, rank, args.train_batch, steps=min(args.steps, 5), warmup=3)
+        except Exception as e:
+            out["train_v3"] = {"error": repr(e)[:300]}
+    if not args.no_ddpm and ws == 1:
+        try:
+            out["config_e"] = config_e(afr)
+        except Exception as e:
+            out["config_e"] = {"error": repr(e)[:300]}
     if rank == 0:
         emit(out)
     if ws > 1:
