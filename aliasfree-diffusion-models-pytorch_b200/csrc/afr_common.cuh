@@ -65,6 +65,35 @@ __device__ __forceinline__ void st4(bf16 *p, float4 v)
     __stcs(reinterpret_cast<uint2 *>(p), r);
 }
 
+// 8 consecutive elements (pointer aligned to 8 elements): one 128-bit access for bf16
+__device__ __forceinline__ void ld8(const float *p, float (&v)[8])
+{
+    const float4 a = ld4(p), b = ld4(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16 *p, float (&v)[8])
+{
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void st8(float *p, const float (&v)[8])
+{
+    st4(p, make_float4(v[0], v[1], v[2], v[3]));
+    st4(p + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+__device__ __forceinline__ void st8(bf16 *p, const float (&v)[8])
+{
+    uint4 r;
+    r.x = pack_bf16x2(v[0], v[1]); r.y = pack_bf16x2(v[2], v[3]);
+    r.z = pack_bf16x2(v[4], v[5]); r.w = pack_bf16x2(v[6], v[7]);
+    __stcs(reinterpret_cast<uint4 *>(p), r);
+}
+
 // shared-memory flavours (no __ldg)
 __device__ __forceinline__ float lds1(const float *p) { return *p; }
 __device__ __forceinline__ float lds1(const bf16 *p)

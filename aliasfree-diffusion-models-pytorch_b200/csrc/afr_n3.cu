@@ -349,6 +349,8 @@ struct TileCfg {
     int Tw, R, P;              // tile width (outputs), rows per chunk, planes per CTA
     int strips;                // Tw / 4 : threads per plane row
     int tiles_x;               // column tiles per plane
+    int ghost;                 // planes wider than one tile: leading strips of every tile that only
+                               // feed the column-0 shuffle of their right neighbour (never stored)
     int nsegs, Hs;             // row segments per plane (blockIdx.y) and their height
     int tile_bytes;            // bytes of one staged box, rounded up to 128
 };
@@ -371,7 +373,7 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
 
     const int tx = (int)(blockIdx.x % cfg.tiles_x);
     const long p0 = (long)(blockIdx.x / cfg.tiles_x) * cfg.P;
-    const int j0 = tx * cfg.Tw;
+    const int j0 = tx * (cfg.Tw - 4 * cfg.ghost) - 4 * cfg.ghost;   // first column of strip 0 (may be < 0)
     const int pitch = cfg.Tw + 2 * HALO, rows = cfg.R + 1;
     const int stage_bytes = NIN * cfg.tile_bytes;
     const uint32_t box_bytes = (uint32_t)(pitch * rows * cfg.P * sizeof(T));
@@ -405,12 +407,14 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     const int s = threadIdx.x % cfg.strips;
     int pl = threadIdx.x / cfg.strips;
     const int j = j0 + 4 * s;
-    const bool valid = (pl < cfg.P) && (p0 + pl < planes) && (j < W);
+    const bool valid = (pl < cfg.P) && (p0 + pl < planes) && (s >= cfg.ghost) && (j < W);
     if (pl >= cfg.P) pl = 0;                        // idle lanes shadow plane 0 of the tile, stores off
     const bool first_col = (j == 0);
-    const bool own0 = (j > 0) && (s == 0 || (threadIdx.x & 31) == 0);
+    // with ghost strips every real strip has its left neighbour in lane-1; otherwise lane 0 of a
+    // warp that does not start a plane row recomputes column 0 itself
+    const bool own0 = (cfg.ghost == 0) && (j > 0) && (s == 0 || (threadIdx.x & 31) == 0);
     const int toff = pl * rows * pitch + HALO + 4 * s;
-    T *dst = out + (p0 + pl) * (long)H * W + j;
+    T *dst = out + (p0 + pl) * (long)H * W + (valid ? j : 0);
 
     float x0[6], x1[6], d0[6], d1[6], m0[9], m1[9];
 #pragma unroll
@@ -492,10 +496,8 @@ up3_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int H, 
             o[2 * c + 1] = fmaf(k.k[2][2], xb[c + 1], t);
         }
         TO *r0 = dst + (long)(2 * i) * W2;
-        st4(r0, make_float4(e[0], e[1], e[2], e[3]));
-        st4(r0 + 4, make_float4(e[4], e[5], e[6], e[7]));
-        st4(r0 + W2, make_float4(o[0], o[1], o[2], o[3]));
-        st4(r0 + W2 + 4, make_float4(o[4], o[5], o[6], o[7]));
+        st8(r0, e);                                  // 8 outputs: 2x128-bit (fp32) or 1x128-bit (bf16)
+        st8(r0 + W2, o);
     }
 }
 
@@ -510,10 +512,11 @@ __device__ __forceinline__ void load9(const T *plane, int row, int H, int W, int
         return;
     }
     const T *p = plane + (long)row * W + c0;
-    float4 a = ld4(p), b = ld4(p + 4);
+    float w[8];
+    ld8(p, w);
     v[0] = has_l ? ld1(p - 1) : 0.f;
-    v[1] = a.x; v[2] = a.y; v[3] = a.z; v[4] = a.w;
-    v[5] = b.x; v[6] = b.y; v[7] = b.z; v[8] = b.w;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c + 1] = w[c];
 }
 
 template <typename T>
@@ -674,7 +677,16 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
     TileCfg c;
     c.Tw = W <= 128 ? W : 128;
     c.strips = c.Tw / 4;
+    // wide planes: tiles of 32 strips whose first 16 bytes' worth of strips are ghosts (1 for fp32,
+    // 2 for bf16 -- keeps every box start 16-byte aligned), see TileCfg::ghost.  Only used when it
+    // does not cost an extra, mostly idle tile (W = 256, 512 split evenly into 128-wide tiles and
+    // keep the recompute branch instead).
+    c.ghost = 0;
     c.tiles_x = (W + c.Tw - 1) / c.Tw;
+    if (W > 128) {
+        const int g = (int)(16 / (4 * es)), stride = c.Tw - 4 * g;
+        if ((W + stride - 1) / stride == c.tiles_x) c.ghost = g;
+    }
     // 128-thread CTAs unless that leaves fewer than ~6 CTAs per SM: long-lived streaming CTAs
     // need a few waves to balance, so small batches of large planes use smaller CTAs
     int th = 128;
@@ -760,7 +772,7 @@ cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, void *out, 
 bool n3_up_supported(int H, int W, const void *in, const void *out, int in_dtype, int out_dtype)
 {
     return H >= 1 && W >= 4 && (W % 4) == 0 && aligned_to(in, 4 * esize(in_dtype)) &&
-           aligned_to(out, 4 * esize(out_dtype));
+           aligned_to(out, 8 * esize(out_dtype));      // 8 outputs per thread row: 128-bit stores
 }
 
 cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,
@@ -783,7 +795,7 @@ cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, con
 
 bool n3_down_supported(int H, int W, const void *in, const void *out, int dtype)
 {
-    return H >= 1 && W >= 8 && (W % 8) == 0 && aligned_to(in, 4 * esize(dtype)) &&
+    return H >= 1 && W >= 8 && (W % 8) == 0 && aligned_to(in, 8 * esize(dtype)) &&     // 8-element loads
            aligned_to(out, 4 * esize(dtype));
 }
 

@@ -113,6 +113,38 @@ def test_state_dict_is_strictly_loadable_from_reference():
         assert [tuple(p.shape) for p in ours.parameters()] == [tuple(p.shape) for p in ref.parameters()]
 
 
+def test_patch_rebinds_reference_names_and_restores():
+    """patch() makes the reference's own UNet build from our block classes (checked on CPU by
+    construction + strict state_dict exchange; the forward needs a GPU) and unpatch() undoes it."""
+    if not os.path.isdir("/root/reference/modules"):
+        pytest.skip("no reference checkout on this machine")
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "imageio"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.path.insert(0, "/root/reference")
+    import modules.ddpm_models as rm
+    import modules.ddpm_utils as ru
+    import aliasfree_b200 as afr
+    orig = (rm.DoubleConv_F, ru.custom_upsample, rm.Diffusion.__dict__["rotate_2d_matrix"])
+    ref_sd = rm.UNet(c_in=3, c_out=3, image_size=16, device="cpu", f_settings=FS, variant=3).state_dict()
+    names = afr.patch()
+    try:
+        assert {"modules.ddpm_models.DoubleConv_F", "modules.ddpm_utils.custom_upsample",
+                "modules.ddpm_utils.custom_downsample", "modules.ddpm_models.Up_FFF",
+                "modules.ddpm_models.Diffusion.rotate_2d_matrix"} <= set(names)
+        net = rm.UNet(c_in=3, c_out=3, image_size=16, device="cpu", f_settings=FS, variant=3)
+        assert isinstance(net.inc, afr.DoubleConv_F) and isinstance(net.down1, afr.Down_FFF)
+        assert isinstance(net.up3.conv[1], afr.DoubleConv_F)
+        net.load_state_dict(ref_sd, strict=True)                 # reference checkpoint -> patched model
+        assert ru.custom_upsample is afr.custom_upsample
+        with pytest.raises(RuntimeError, match="CUDA"):          # and it really is our (GPU-only) path
+            net(torch.randn(1, 3, 16, 16), torch.tensor([5]))
+    finally:
+        afr.unpatch()
+    assert (rm.DoubleConv_F, ru.custom_upsample, rm.Diffusion.__dict__["rotate_2d_matrix"]) == orig
+
+
 def test_variant0_unet_runs_on_cpu_and_matches_reference():
     """Variant 0 has no filters, so the wiring itself can be checked on CPU against the reference."""
     if not os.path.isdir("/root/reference/modules"):
