@@ -256,3 +256,58 @@ def test_ddpm_update(afr):
         assert (got - want).abs().max().item() <= 1e-6
         got = afr.ddpm_update_(x.clone(), e, None, 1.01, 0.3, 0.0)
         assert (got - 1.01 * (x - 0.3 * e)).abs().max().item() <= 1e-6
+
+
+def test_deterministic_and_stream_ordered(afr, oracle):
+    """Bitwise repeatable (no atomics), honours the caller's current stream, capturable in a CUDA graph."""
+    k = oracle.lowpass_taps(np.pi / 2, 3, 2.0)
+    x = torch.randn(8, 16, 32, 32, device="cuda")
+    dy = torch.randn_like(x)
+    ref = afr.filtered_gelu(x, k, k)
+    for _ in range(3):
+        assert torch.equal(afr.filtered_gelu(x, k, k), ref)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        z = x * 2.0                                    # produced on the side stream ...
+        y_side = afr.filtered_gelu(z, k, k)            # ... and consumed by our kernel on the same stream
+    torch.cuda.current_stream().wait_stream(side)
+    assert relmax(host(y_side), oracle.filtered_gelu(host(x) * 2.0, k, k)) <= FP32_TOL
+    # graph capture + replay with new data in the static input
+    static_x = x.clone()
+    g = torch.cuda.CUDAGraph()
+    s2 = torch.cuda.Stream(); s2.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s2):
+        afr.ops._fgelu_bwd(static_x, None, dy, afr.Taps(k), afr.Taps(k))       # warm-up
+    torch.cuda.current_stream().wait_stream(s2)
+    with torch.cuda.graph(g):
+        static_out = afr.ops._fgelu_bwd(static_x, None, dy, afr.Taps(k), afr.Taps(k))
+    static_x.copy_(x * 0.5)
+    g.replay()
+    torch.cuda.synchronize()
+    assert relmax(host(static_out), oracle.filtered_gelu_bwd(host(x) * 0.5, host(dy), k, k)) <= FP32_TOL
+
+
+@pytest.mark.parametrize("shape", [(5, 1, 64, 24), (3, 7, 8, 48), (2, 3, 100, 136), (1, 5, 18, 8), (7, 1, 2, 16)])
+def test_streaming_kernel_partial_tiles(afr, oracle, shape):
+    """Shapes that exercise the row-streaming kernel's corners: planes not a multiple of P, strip
+    counts that do not divide a warp (lane-0 recompute), ghost-strip column tiles, row segments,
+    last chunk partly outside the plane, residual + adjoint with three staged tensors."""
+    rng = np.random.default_rng(11)
+    ku = (oracle.lowpass_taps(np.pi / 2, 3, 2.0) + 0.03 * rng.standard_normal((3, 3))).astype(np.float32)
+    kd = (oracle.lowpass_taps(np.pi / 3, 3, None) + 0.03 * rng.standard_normal((3, 3))).astype(np.float32)
+    x, r, dy = (rng.standard_normal(shape).astype(np.float32) for _ in range(3))
+    afr.set_path("tma")
+    try:
+        xt, rt = dev(x, grad=True), dev(r, grad=True)
+        y = afr.filtered_gelu(xt, ku, kd, residual=rt)
+        assert afr.last_kernel() == "fgelu3_tma_kernel"
+        assert relmax(host(y), oracle.filtered_gelu(x + r, ku, kd)) <= FP32_TOL
+        gx, gr = torch.autograd.grad(y, (xt, rt), dev(dy))
+        assert relmax(host(gx), oracle.filtered_gelu_bwd(x + r, dy, ku, kd)) <= FP32_TOL
+        xb = dev(x, torch.bfloat16)
+        if shape[-1] % 8 == 0:
+            yb = afr.filtered_gelu(xb, ku, kd)
+            assert relmax(host(yb), oracle.filtered_gelu(host(xb), ku, kd)) <= BF16_TOL
+    finally:
+        afr.set_path("auto")
