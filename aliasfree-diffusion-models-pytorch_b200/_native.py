@@ -57,21 +57,23 @@ def _declare(L):
     L.afr_down2x_fwd.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci, vp]
     L.afr_down2x_bwd.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci, vp]
     L.afr_filtered_gelu_fwd.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
+    L.afr_filtered_gelu_affine_fwd.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
+    L.afr_groupnorm1_affine.argtypes = [vp, vp, vp, cf, vp, vp, ci, ci, ci, ci, ci, vp]
     L.afr_filtered_gelu_bwd.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
     L.afr_rotate_periodic_cubic.argtypes = [vp, vp, ci, ci, ci, ci, cd, ci, vp]
     L.afr_ddpm_update.argtypes = [vp, vp, vp, i64, cf, cf, cf, vp]
     L.afr_ddpm_update_table.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     for n in ("afr_up2x_fwd", "afr_up2x_bwd", "afr_down2x_fwd", "afr_down2x_bwd",
-              "afr_filtered_gelu_fwd", "afr_filtered_gelu_bwd", "afr_rotate_periodic_cubic",
-              "afr_ddpm_update", "afr_ddpm_update_table"):
+              "afr_filtered_gelu_fwd", "afr_filtered_gelu_bwd", "afr_filtered_gelu_affine_fwd", "afr_groupnorm1_affine",
+              "afr_rotate_periodic_cubic", "afr_ddpm_update", "afr_ddpm_update_table"):
         getattr(L, n).restype = ci
     return L
 
 
 EXPORTS = ("afr_version", "afr_last_error", "afr_status_string", "afr_set_path", "afr_last_kernel",
            "afr_launch_count", "afr_up2x_fwd", "afr_up2x_bwd", "afr_down2x_fwd", "afr_down2x_bwd",
-           "afr_filtered_gelu_fwd", "afr_filtered_gelu_bwd", "afr_rotate_periodic_cubic",
-           "afr_ddpm_update", "afr_ddpm_update_table")
+           "afr_filtered_gelu_fwd", "afr_filtered_gelu_bwd", "afr_filtered_gelu_affine_fwd", "afr_groupnorm1_affine",
+           "afr_rotate_periodic_cubic", "afr_ddpm_update", "afr_ddpm_update_table")
 
 
 def lib():

@@ -21,6 +21,17 @@ from . import ops
 from .filters import taps_from_settings
 
 
+# Inference (no-grad) forward of DoubleConv_F folds each GroupNorm's normalise + affine into the
+# fused activation kernel that follows it; set to False to always run nn.GroupNorm separately.
+FUSE_GROUPNORM_INFERENCE = True
+
+
+def _groupnorm1_affine(h, norm):
+    """GroupNorm(1, C) as a per-(sample, channel) affine: returns (scale, shift), both [B, C] fp32,
+    with  norm(h) == h * scale[:, :, None, None] + shift[:, :, None, None]  (one reduction kernel)."""
+    return ops.groupnorm1_affine(h, norm.weight, norm.bias, norm.eps)
+
+
 def _conv3(cin, cout):
     return nn.Conv2d(cin, cout, kernel_size=3, padding=1, bias=False)
 
@@ -83,14 +94,31 @@ class DoubleConv_F(nn.Module):
             self._taps = (key, ops.Taps(self.sinc_filter), ops.Taps(self.jinc_filter))
         return self._taps[1], self._taps[2]
 
+    def _can_fuse_norm(self, x):
+        return (FUSE_GROUPNORM_INFERENCE and not torch.is_grad_enabled() and x.is_cuda and up_is_n3(self)
+                and x.shape[-1] % 4 == 0 and x.dtype in (torch.float32, torch.bfloat16)
+                and self.norm1.num_groups == 1 and self.norm1.affine)
+
     def forward(self, x):
         up, dn = self._filters()
+        if self._can_fuse_norm(x):
+            # inference: GroupNorm statistics by torch, normalise + affine inside the activation kernel
+            h = self.conv1(x)
+            h = ops.filtered_gelu_affine(h, *_groupnorm1_affine(h, self.norm1), up, dn)
+            h = self.conv2(h)
+            if self.residual:
+                return ops.filtered_gelu_affine(h, *_groupnorm1_affine(h, self.norm2), up, dn, residual=x)
+            return self.norm2(h)
         h = self.norm1(self.conv1(x))
         h = ops.filtered_gelu(h, up, dn)
         h = self.norm2(self.conv2(h))
         if self.residual:
             h = ops.filtered_gelu(h, up, dn, residual=x)     # gelu-filter(x + h), add fused
         return h
+
+
+def up_is_n3(block):
+    return block.sinc_filter.shape[-1] == 3 and block.jinc_filter.shape[-1] == 3
 
 
 class _TimeConditioned(nn.Module):

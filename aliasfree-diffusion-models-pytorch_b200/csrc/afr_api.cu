@@ -236,7 +236,8 @@ int afr_down2x_bwd(const void *dy, void *dv, int B, int C, int H, int W, const f
 
 static int fused_common(const void *x, const void *residual, const void *dy, void *out, int B, int C,
                         int H, int W, const float *taps_up, int N_up, const float *taps_down,
-                        int N_down, int dtype, void *stream, bool bwd)
+                        int N_down, int dtype, void *stream, bool bwd, const float *scale = nullptr,
+                        const float *shift = nullptr)
 {
     if (int rc = check_common(B, C, H, W, taps_up, N_up)) return rc;
     if (int rc = check_common(B, C, H, W, taps_down, N_down)) return rc;
@@ -262,10 +263,13 @@ static int fused_common(const void *x, const void *residual, const void *dy, voi
             for (int i = 0; i < 9; ++i) kU.k[i / 3][i % 3] *= AFR_KAPPA;
         set_taps3(kG, taps_down, true);
         set_taps3(kB, bwd ? taps_up : taps_down, bwd);
-        return cuda_status(n3_fgelu(x, residual, dy, out, planes, H, W, kU, kG, kB, bwd, dtype, use_tma, s,
-                                    &g_last_kernel),
+        return cuda_status(n3_fgelu(x, residual, dy, scale, shift, out, planes, H, W, kU, kG, kB, bwd, dtype,
+                                    use_tma, s, &g_last_kernel),
                            "fgelu3 kernel");
     }
+    if (scale)
+        return fail(AFR_ERR_UNSUPPORTED, "affine fusion needs the N==3 kernels (N_up=%d N_down=%d H=%d W=%d)", N_up,
+                    N_down, H, W);
     if (path == AFR_PATH_TMA || path == AFR_PATH_DIRECT)
         return fail(AFR_ERR_UNSUPPORTED, "N==3 path forced but N_up=%d N_down=%d H=%d W=%d not eligible", N_up, N_down, H, W);
     TapsG tU, tG, tB;
@@ -283,6 +287,16 @@ int afr_filtered_gelu_fwd(const void *x, const void *residual, void *y, int B, i
 {
     return fused_common(x, residual, nullptr, y, B, C, H, W, taps_up, N_up, taps_down, N_down, dtype,
                         stream, false);
+}
+
+int afr_filtered_gelu_affine_fwd(const void *x, const void *residual, const float *scale_dev,
+                                 const float *shift_dev, void *y, int B, int C, int H, int W,
+                                 const float *taps_up, int N_up, const float *taps_down, int N_down,
+                                 int dtype, void *stream)
+{
+    if (!scale_dev || !shift_dev) return fail(AFR_ERR_NULL_POINTER, "scale or shift is NULL");
+    return fused_common(x, residual, nullptr, y, B, C, H, W, taps_up, N_up, taps_down, N_down, dtype,
+                        stream, false, scale_dev, shift_dev);
 }
 
 int afr_filtered_gelu_bwd(const void *x, const void *residual, const void *dy, void *dx, int B, int C,
@@ -309,6 +323,24 @@ int afr_rotate_periodic_cubic(const void *x, void *y, int B, int C, int H, int W
     return cuda_status(rotate_periodic_cubic((const float *)x, (float *)y, planes, H, W, degrees,
                                              (cudaStream_t)stream),
                        "rotate_kernel");
+}
+
+int afr_groupnorm1_affine(const void *x, const float *gamma_dev, const float *beta_dev, float eps,
+                          float *scale_dev, float *shift_dev, int B, int C, int H, int W, int dtype,
+                          void *stream)
+{
+    if (B < 0 || C < 1 || H < 1 || W < 1) return fail(AFR_ERR_BAD_SHAPE, "bad shape");
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if (B == 0) return AFR_OK;
+    if (!x || !gamma_dev || !beta_dev || !scale_dev || !shift_dev) return fail(AFR_ERR_NULL_POINTER, "NULL pointer");
+    const long hw = (long)H * W;
+    if (((long)C * hw) % 4 != 0 || (reinterpret_cast<uintptr_t>(x) % (4 * esz(dtype))) != 0)
+        return fail(AFR_ERR_UNSUPPORTED, "C*H*W must be a multiple of 4 and x aligned to 4 elements");
+    begin_call();
+    g_last_kernel = "groupnorm1_affine_kernel";
+    return cuda_status(groupnorm1_affine(x, gamma_dev, beta_dev, eps, scale_dev, shift_dev, B, C, hw, dtype,
+                                         (cudaStream_t)stream),
+                       "groupnorm1_affine_kernel");
 }
 
 int afr_ddpm_update(void *x, const void *eps, const void *noise, int64_t n, float ca, float cb,

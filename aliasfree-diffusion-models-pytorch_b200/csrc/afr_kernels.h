@@ -23,9 +23,9 @@ cudaError_t generic_fgelu(const void *x, const void *res, const void *dy, void *
 bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype);
 bool n3_fgelu_tma_supported(long planes, int H, int W, const void *const *ptrs, int nptrs, int dtype,
                             int n_inputs);
-cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, void *out, long planes,
-                     int H, int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd,
-                     int dtype, bool use_tma, cudaStream_t s, const char **kernel_name);
+cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, const float *scale, const float *shift,
+                     void *out, long planes, int H, int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB,
+                     bool bwd, int dtype, bool use_tma, cudaStream_t s, const char **kernel_name);
 // up-like with N==3: in [planes,H,W] -> out [planes,2H,2W]
 bool n3_up_supported(int H, int W, const void *in, const void *out, int in_dtype, int out_dtype);
 cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,
@@ -38,6 +38,8 @@ cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, c
 // afr_rotate.cu
 cudaError_t rotate_periodic_cubic(const float *x, float *y, long planes, int H, int W,
                                   double degrees, cudaStream_t s);
+cudaError_t groupnorm1_affine(const void *x, const float *gamma, const float *beta, float eps, float *scale,
+                              float *shift, long B, int C, long hw, int dtype, cudaStream_t s);
 cudaError_t ddpm_update(float *x, const float *eps, const float *noise, long n, float ca,
                         float cb, float cc, const float *table_dev, const int *step_dev, cudaStream_t s);
 

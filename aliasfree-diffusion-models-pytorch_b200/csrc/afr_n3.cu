@@ -93,11 +93,20 @@ __device__ __forceinline__ void act_col0_pair(float (&ue)[9], float (&uo)[9], fl
 // ---------------------------------------------------------------------------------
 // row sources
 // ---------------------------------------------------------------------------------
-template <typename T, bool kRes>
+// Optional per-plane affine x * a + b folded into the load (the normalise + affine step of the
+// GroupNorm that precedes the activation, modules/ddpm_utils.py:122, 127).  Zero padding applies
+// to the normalised tensor, so `b` is added only to samples inside the plane: bc / bl / br are the
+// shift for the 4 centre columns, the left and the right neighbour (0 where that column is outside).
+struct Affine {
+    float a, bc, bl, br;
+};
+
+template <typename T, bool kRes, bool kAff = false>
 struct GlobalRows {
     const T *x;   // plane base, already offset to column j
     const T *r;   // residual plane (kRes), same offset
     int H, W, j;
+    Affine f;
     __device__ __forceinline__ void load(int row, float (&v)[6]) const
     {
         if (row < 0 || row >= H) {
@@ -109,6 +118,11 @@ struct GlobalRows {
         float4 c4 = ld4(x + off);
         float l = (j > 0) ? ld1(x + off - 1) : 0.f;
         float rr = (j + 4 < W) ? ld1(x + off + 4) : 0.f;
+        if (kAff) {
+            c4.x = fmaf(c4.x, f.a, f.bc); c4.y = fmaf(c4.y, f.a, f.bc);
+            c4.z = fmaf(c4.z, f.a, f.bc); c4.w = fmaf(c4.w, f.a, f.bc);
+            l = fmaf(l, f.a, f.bl); rr = fmaf(rr, f.a, f.br);
+        }
         if (kRes) {
             float4 q4 = ld4(r + off);
             c4.x += q4.x; c4.y += q4.y; c4.z += q4.z; c4.w += q4.w;
@@ -119,16 +133,25 @@ struct GlobalRows {
     }
 };
 
-template <typename T, bool kRes>
+template <typename T, bool kRes, bool kAff = false>
 struct TileRows {
     const T *x;   // shared tile, pointing at (tile row 0, this thread's column j)
     const T *r;
     int pitch, row0;   // row0 = global row index of tile row 0
+    int H;             // plane height (kAff: rows outside the plane must stay exactly zero)
+    Affine f;
     __device__ __forceinline__ void load(int row, float (&v)[6]) const
     {
         const int off = (row - row0) * pitch;
         float4 c4 = lds4(x + off);
         float l = lds1(x + off - 1), rr = lds1(x + off + 4);
+        if (kAff) {                                   // staged zeros (TMA OOB fill) times a stay zero
+            const bool in = (unsigned)row < (unsigned)H;
+            const float bc = in ? f.bc : 0.f, bl = in ? f.bl : 0.f, br = in ? f.br : 0.f;
+            c4.x = fmaf(c4.x, f.a, bc); c4.y = fmaf(c4.y, f.a, bc);
+            c4.z = fmaf(c4.z, f.a, bc); c4.w = fmaf(c4.w, f.a, bc);
+            l = fmaf(l, f.a, bl); rr = fmaf(rr, f.a, br);
+        }
         if (kRes) {
             float4 q4 = lds4(r + off);
             c4.x += q4.x; c4.y += q4.y; c4.z += q4.z; c4.w += q4.w;
@@ -137,6 +160,20 @@ struct TileRows {
         v[0] = l; v[1] = c4.x; v[2] = c4.y; v[3] = c4.z; v[4] = c4.w; v[5] = rr;
     }
 };
+
+__device__ __forceinline__ Affine make_affine(const float *scale, const float *shift, long p, bool plane_ok,
+                                              int j, int W)
+{
+    Affine f = {0.f, 0.f, 0.f, 0.f};
+    if (scale && plane_ok) {
+        const float b = __ldg(shift + p);
+        f.a = __ldg(scale + p);
+        f.bc = (j >= 0 && j < W) ? b : 0.f;
+        f.bl = (j > 0 && j <= W) ? b : 0.f;
+        f.br = (j + 4 >= 0 && j + 4 < W) ? b : 0.f;
+    }
+    return f;
+}
 
 // ---------------------------------------------------------------------------------
 // the strip core
@@ -265,9 +302,10 @@ __device__ __forceinline__ void strip_core(const SX &sx, const SD &sd, TO *__res
 // ---------------------------------------------------------------------------------
 // direct kernel
 // ---------------------------------------------------------------------------------
-template <typename T, bool kBwd, bool kRes>
+template <typename T, bool kBwd, bool kRes, bool kAff>
 __global__ void __launch_bounds__(256)
 fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T *__restrict__ dy,
+                     const float *__restrict__ scale, const float *__restrict__ shift,
                      T *__restrict__ out, long planes, int H, int W, int strips, int nseg, int R,
                      const __grid_constant__ Taps3 kU, const __grid_constant__ Taps3 kG,
                      const __grid_constant__ Taps3 kB)
@@ -283,8 +321,9 @@ fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T
     const long p = pu;
     const int j = 4 * s, i0 = seg * R, i1 = min(H, i0 + R);
     const long base = p * (long)H * W + j;
-    GlobalRows<T, kRes> sx{x + base, kRes ? res + base : nullptr, H, W, j};
-    GlobalRows<T, false> sd{kBwd ? dy + base : nullptr, nullptr, H, W, j};
+    GlobalRows<T, kRes, kAff> sx{x + base, kRes ? res + base : nullptr, H, W, j,
+                                 make_affine(kAff ? scale : nullptr, shift, p, true, j, W)};
+    GlobalRows<T, false> sd{kBwd ? dy + base : nullptr, nullptr, H, W, j, Affine{0.f, 0.f, 0.f, 0.f}};
     const bool own0 = (s > 0) && ((threadIdx.x & 31) == 0);
     strip_core<kBwd>(sx, sd, out + base, W, i0, i1, R, valid, j == 0, own0, kU, kG, kB);
 }
@@ -359,10 +398,11 @@ struct TileCfg {
 // mid row and input row simply stay in registers across chunks, so there is no per-segment
 // start-up work at all, and the next two chunks are always in flight (2-stage TMA/mbarrier
 // ring) while the current one is being computed.
-template <typename T, bool kBwd, bool kRes>
+template <typename T, bool kBwd, bool kRes, bool kAff>
 __global__ void __launch_bounds__(128)
 fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mres,
-                  const __grid_constant__ CUtensorMap mdy, T *__restrict__ out, long planes, int H,
+                  const __grid_constant__ CUtensorMap mdy, const float *__restrict__ scale,
+                  const float *__restrict__ shift, T *__restrict__ out, long planes, int H,
                   int W, const __grid_constant__ TileCfg cfg, const __grid_constant__ Taps3 kU,
                   const __grid_constant__ Taps3 kG, const __grid_constant__ Taps3 kB)
 {
@@ -415,6 +455,7 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     const bool own0 = (cfg.ghost == 0) && (j > 0) && (s == 0 || (threadIdx.x & 31) == 0);
     const int toff = pl * rows * pitch + HALO + 4 * s;
     T *dst = out + (p0 + pl) * (long)H * W + (valid ? j : 0);
+    const Affine aff = make_affine(kAff ? scale : nullptr, shift, p0 + pl, p0 + pl < planes, j, W);
 
     float x0[6], x1[6], d0[6], d1[6], m0[9], m1[9];
 #pragma unroll
@@ -428,8 +469,8 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
         const T *rs = reinterpret_cast<const T *>(base + (kRes ? cfg.tile_bytes : 0));
         const T *ds = reinterpret_cast<const T *>(base + (kRes ? 2 : 1) * cfg.tile_bytes);
         const int r0 = istart + k * cfg.R;
-        TileRows<T, kRes> sx{xs + toff, rs + toff, pitch, r0};
-        TileRows<T, false> sd{ds + toff, nullptr, pitch, r0};
+        TileRows<T, kRes, kAff> sx{xs + toff, rs + toff, pitch, r0, H, aff};
+        TileRows<T, false> sd{ds + toff, nullptr, pitch, r0, H, Affine{0.f, 0.f, 0.f, 0.f}};
         mbar_wait(&full[k & 1], (k >> 1) & 1);
         if (k == 0) {
             sx.load(r0, x0);
@@ -642,18 +683,19 @@ static bool make_plane_map(CUtensorMap *m, const void *base, long planes, int H,
 
 static inline int pick_rows(int H) { return H < 8 ? H : 8; }
 
-template <typename T, bool kBwd, bool kRes>
-static cudaError_t launch_direct(const void *x, const void *res, const void *dy, void *out,
-                                 long planes, int H, int W, const Taps3 &kU, const Taps3 &kG,
-                                 const Taps3 &kB, cudaStream_t s)
+template <typename T, bool kBwd, bool kRes, bool kAff>
+static cudaError_t launch_direct(const void *x, const void *res, const void *dy, const float *scale,
+                                 const float *shift, void *out, long planes, int H, int W,
+                                 const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, cudaStream_t s)
 {
     const int strips = W / 4, R = pick_rows(H), nseg = (H + R - 1) / R;
     const long total = planes * (long)strips * nseg;
     const int block = 128;
     const long grid = (total + block - 1) / block;
     if (total >= 0x7fffffffL) { set_detail("tensor too large for the direct kernel's 32-bit indexing"); return cudaErrorInvalidConfiguration; }
-    fgelu3_direct_kernel<T, kBwd, kRes><<<(unsigned)grid, block, 0, s>>>(
-        (const T *)x, (const T *)res, (const T *)dy, (T *)out, planes, H, W, strips, nseg, R, kU, kG, kB);
+    fgelu3_direct_kernel<T, kBwd, kRes, kAff><<<(unsigned)grid, block, 0, s>>>(
+        (const T *)x, (const T *)res, (const T *)dy, scale, shift, (T *)out, planes, H, W, strips, nseg, R,
+        kU, kG, kB);
     return cudaGetLastError();
 }
 
@@ -718,10 +760,10 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
     return false;
 }
 
-template <typename T, bool kBwd, bool kRes>
-static cudaError_t launch_tma(const void *x, const void *res, const void *dy, void *out,
-                              long planes, int H, int W, int dtype, const Taps3 &kU,
-                              const Taps3 &kG, const Taps3 &kB, cudaStream_t s)
+template <typename T, bool kBwd, bool kRes, bool kAff>
+static cudaError_t launch_tma(const void *x, const void *res, const void *dy, const float *scale,
+                              const float *shift, void *out, long planes, int H, int W, int dtype,
+                              const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, cudaStream_t s)
 {
     const int nin = 1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0);
     int threads; TileCfg cfg;
@@ -737,35 +779,36 @@ static cudaError_t launch_tma(const void *x, const void *res, const void *dy, vo
     if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
     const dim3 grid3((unsigned)grid, (unsigned)cfg.nsegs);
     const size_t smem = (size_t)cfg.tile_bytes * nin * 2;
-    auto kern = fgelu3_tma_kernel<T, kBwd, kRes>;
+    auto kern = fgelu3_tma_kernel<T, kBwd, kRes, kAff>;
     static bool attr_set = false;     // per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) { set_detail("cudaFuncSetAttribute(max dynamic smem) failed"); return e; }
         attr_set = true;
     }
-    kern<<<grid3, threads, smem, s>>>(mx, mres, mdy, (T *)out, planes, H, W, cfg, kU, kG, kB);
+    kern<<<grid3, threads, smem, s>>>(mx, mres, mdy, scale, shift, (T *)out, planes, H, W, cfg, kU, kG, kB);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         set_detail("launch grid=%ld block=%d smem=%zu tile Tw=%d R=%d P=%d", grid, threads, smem, cfg.Tw, cfg.R, cfg.P);
     return e;
 }
 
-cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, void *out, long planes, int H,
-                     int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd, int dtype,
-                     bool use_tma, cudaStream_t s, const char **kernel_name)
+cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, const float *scale, const float *shift,
+                     void *out, long planes, int H, int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB,
+                     bool bwd, int dtype, bool use_tma, cudaStream_t s, const char **kernel_name)
 {
-#define AFR_GO(T, B, R)                                                                           \
-    return use_tma ? launch_tma<T, B, R>(x, res, dy, out, planes, H, W, dtype, kU, kG, kB, s)     \
-                   : launch_direct<T, B, R>(x, res, dy, out, planes, H, W, kU, kG, kB, s)
+#define AFR_GO(T, B, R, A)                                                                                   \
+    return use_tma ? launch_tma<T, B, R, A>(x, res, dy, scale, shift, out, planes, H, W, dtype, kU, kG, kB, s) \
+                   : launch_direct<T, B, R, A>(x, res, dy, scale, shift, out, planes, H, W, kU, kG, kB, s)
+#define AFR_GO_T(T)                                                                                          \
+    if (bwd) { if (res) { AFR_GO(T, true, true, false); } else { AFR_GO(T, true, false, false); } }          \
+    else if (scale) { if (res) { AFR_GO(T, false, true, true); } else { AFR_GO(T, false, false, true); } }   \
+    else { if (res) { AFR_GO(T, false, true, false); } else { AFR_GO(T, false, false, false); } }
     if (kernel_name) *kernel_name = use_tma ? "fgelu3_tma_kernel" : "fgelu3_direct_kernel";
-    if (dtype == AFR_F32) {
-        if (bwd) { if (res) { AFR_GO(float, true, true); } else { AFR_GO(float, true, false); } }
-        else     { if (res) { AFR_GO(float, false, true); } else { AFR_GO(float, false, false); } }
-    } else {
-        if (bwd) { if (res) { AFR_GO(bf16, true, true); } else { AFR_GO(bf16, true, false); } }
-        else     { if (res) { AFR_GO(bf16, false, true); } else { AFR_GO(bf16, false, false); } }
-    }
+    if (bwd && scale) { set_detail("affine fusion is forward-only"); return cudaErrorNotSupported; }
+    if (dtype == AFR_F32) { AFR_GO_T(float) }
+    AFR_GO_T(bf16)
+#undef AFR_GO_T
 #undef AFR_GO
 }
 

@@ -107,6 +107,77 @@ cudaError_t rotate_periodic_cubic(const float *x, float *y, long planes, int H, 
     return cudaGetLastError();
 }
 
+// GroupNorm(1, C) statistics -> per-(sample, channel) affine for the fused activation kernel:
+//   scale[b][c] = gamma[c] * rstd[b],  shift[b][c] = beta[c] - mean[b] * scale[b][c].
+// One CTA per sample; two passes over the sample (mean, then centred second moment -- the second
+// pass hits L2), per-thread fp32 partials, warp-shuffle + shared-memory reduction in double.
+template <typename T>
+__device__ __forceinline__ float4 ldv4(const T *p);
+template <>
+__device__ __forceinline__ float4 ldv4<float>(const float *p) { return ld4(p); }
+template <>
+__device__ __forceinline__ float4 ldv4<bf16>(const bf16 *p) { return ld4(p); }
+
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();                       // red may still be read from a previous call
+    if ((threadIdx.x & 31) == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += red[i];
+    return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+groupnorm1_affine_kernel(const T *__restrict__ x, const float *__restrict__ gamma,
+                         const float *__restrict__ beta, float eps, float *__restrict__ scale,
+                         float *__restrict__ shift, int C, long n_per_sample)
+{
+    __shared__ double red[32];
+    const long b = blockIdx.x;
+    const T *src = x + b * n_per_sample;
+    const long n4 = n_per_sample / 4;      // launcher guarantees n_per_sample % 4 == 0
+    float s = 0.f;
+    for (long i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = ldv4<T>(src + 4 * i);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    const double mean = block_sum((double)s, red) / (double)n_per_sample;
+    const float mf = (float)mean;
+    float q = 0.f;
+    for (long i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = ldv4<T>(src + 4 * i);
+        const float a = v.x - mf, c = v.y - mf, d = v.z - mf, e = v.w - mf;
+        q += (a * a + c * c) + (d * d + e * e);
+    }
+    // sum (x - mf)^2 = sum (x - mean)^2 + n (mean - mf)^2 ; the correction is ~1e-16, dropped
+    const double var = block_sum((double)q, red) / (double)n_per_sample;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float sc = __ldg(gamma + c) * rstd;
+        scale[b * C + c] = sc;
+        shift[b * C + c] = __ldg(beta + c) - mf * sc;
+    }
+}
+
+cudaError_t groupnorm1_affine(const void *x, const float *gamma, const float *beta, float eps, float *scale,
+                              float *shift, long B, int C, long hw, int dtype, cudaStream_t s)
+{
+    if (B > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    const long n = (long)C * hw;
+    // few samples: one big CTA per sample (latency); many samples: 256-thread CTAs (occupancy)
+    const int threads = (B < 2 * 148 && n >= 8192) ? 1024 : 256;
+    if (dtype == AFR_F32)
+        groupnorm1_affine_kernel<float><<<(unsigned)B, threads, 0, s>>>((const float *)x, gamma, beta, eps, scale, shift, C, n);
+    else
+        groupnorm1_affine_kernel<bf16><<<(unsigned)B, threads, 0, s>>>((const bf16 *)x, gamma, beta, eps, scale, shift, C, n);
+    return cudaGetLastError();
+}
+
 // x <- ca * (x - cb * eps) + cc * noise      (modules/ddpm_models.py:374)
 __global__ void __launch_bounds__(256)
 ddpm_update_kernel(float *__restrict__ x, const float *__restrict__ eps,

@@ -185,6 +185,51 @@ def filtered_gelu(x, filt_up, filt_down, residual=None):
     return _FilteredGelu.apply(x, residual, _taps(filt_up), _taps(filt_down))
 
 
+def filtered_gelu_affine(x, scale, shift, filt_up, filt_down, residual=None):
+    """Inference-only: ``filtered_gelu(x * scale[:, :, None, None] + shift[:, :, None, None] + residual)``
+    in one kernel -- the normalise + affine step of the GroupNorm that precedes the activation
+    (modules/ddpm_utils.py:122-125, 127-131) is folded into the kernel's load.  ``scale`` / ``shift``:
+    float32 CUDA tensors [B, C].  No autograd; raises ``NotImplementedError`` for shapes / filter sizes
+    the fused kernels do not cover (callers fall back to GroupNorm + ``filtered_gelu``)."""
+    x = _require(x)
+    if torch.is_grad_enabled() and (x.requires_grad or scale.requires_grad or shift.requires_grad):
+        raise RuntimeError("afr: filtered_gelu_affine is forward-only (use GroupNorm + filtered_gelu to train)")
+    B, C, H, W = x.shape
+    ku, kd = _taps(filt_up), _taps(filt_down)
+    if ku.n != 3 or kd.n != 3 or W % 4 != 0:
+        raise NotImplementedError("afr: affine fusion needs N == 3 filters and W % 4 == 0")
+    scale = scale.detach().to(torch.float32).contiguous()
+    shift = shift.detach().to(torch.float32).contiguous()
+    if tuple(scale.shape) != (B, C) or tuple(shift.shape) != (B, C) or not scale.is_cuda or not shift.is_cuda:
+        raise ValueError("afr: scale and shift must be CUDA tensors of shape [B, C]")
+    if residual is not None:
+        residual = _require(residual, "residual")
+        if residual.shape != x.shape or residual.dtype != x.dtype:
+            raise ValueError("afr: residual must match x in shape and dtype")
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _check(_native.lib().afr_filtered_gelu_affine_fwd(
+            x.data_ptr(), None if residual is None else residual.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+            y.data_ptr(), B, C, H, W, ku.ptr, ku.n, kd.ptr, kd.n, _DT[x.dtype], _stream(x)))
+    return y
+
+
+def groupnorm1_affine(x, weight, bias, eps):
+    """Statistics of ``GroupNorm(1, C)`` as the [B, C] (scale, shift) pair that
+    ``filtered_gelu_affine`` consumes, in ONE kernel.  Forward only."""
+    x = _require(x)
+    B, C, H, W = x.shape
+    w = weight.detach().to(torch.float32).contiguous()
+    b = bias.detach().to(torch.float32).contiguous()
+    scale = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    shift = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(_native.lib().afr_groupnorm1_affine(x.data_ptr(), w.data_ptr(), b.data_ptr(), float(eps),
+                                                   scale.data_ptr(), shift.data_ptr(), B, C, H, W,
+                                                   _DT[x.dtype], _stream(x)))
+    return scale, shift
+
+
 def custom_upsample(x, sinc_filter, factor=2):
     """Signature of modules/filtrs.py:79.  Like the reference, the result is float32
     whatever the input dtype (filtrs.py:85 allocates an fp32 buffer)."""

@@ -92,6 +92,24 @@ int afr_filtered_gelu_fwd(const void *x, const void *residual, void *y,
                           const float *taps_up, int N_up, const float *taps_down, int N_down,
                           int dtype, void *stream);
 
+/* Forward with the normalise + affine step of the preceding GroupNorm(1, C) folded into the load
+ * (modules/ddpm_utils.py:122-125 and 127-131):  y = filtered_gelu(x * scale[b,c] + shift[b,c] (+ residual)).
+ * scale_dev / shift_dev: DEVICE float32 [B*C] (gamma_c * rstd_b and beta_c - mean_b * gamma_c * rstd_b).
+ * The conv zero padding applies to the normalised tensor, exactly as upstream.  Inference path:
+ * there is no adjoint; N_up == N_down == 3 and W % 4 == 0 required (AFR_ERR_UNSUPPORTED otherwise). */
+int afr_filtered_gelu_affine_fwd(const void *x, const void *residual, const float *scale_dev,
+                                 const float *shift_dev, void *y, int B, int C, int H, int W,
+                                 const float *taps_up, int N_up, const float *taps_down, int N_down,
+                                 int dtype, void *stream);
+
+/* Statistics half of GroupNorm(1, C) (modules/ddpm_utils.py:113, 116): per sample mean / rstd over
+ * (C, H, W), returned as the per-(sample, channel) affine consumed by afr_filtered_gelu_affine_fwd:
+ * scale[b][c] = gamma[c] * rstd[b], shift[b][c] = beta[c] - mean[b] * scale[b][c]  (DEVICE fp32 [B*C]).
+ * gamma_dev / beta_dev: DEVICE fp32 [C].  C*H*W must be a multiple of 4. */
+int afr_groupnorm1_affine(const void *x, const float *gamma_dev, const float *beta_dev, float eps,
+                          float *scale_dev, float *shift_dev, int B, int C, int H, int W, int dtype,
+                          void *stream);
+
 /* adjoint of the above wrt (x + residual): recomputes u from x, reads dy, writes dx
  * (d/dx and d/dresidual are the same tensor).  No saved 4x intermediates. */
 int afr_filtered_gelu_bwd(const void *x, const void *residual, const void *dy, void *dx,

@@ -79,6 +79,66 @@ def test_unet_matches_reference(afr, variant, size, c):
             assert relmax(host(params[name].grad), g[key]) <= UNET_TOL, name
 
 
+def test_groupnorm_fusion_inference_matches_reference(afr):
+    """Under no_grad DoubleConv_F folds GroupNorm's normalise + affine into the fused kernel;
+    outputs must still match the reference fixtures, and equal the unfused path."""
+    from aliasfree_b200 import blocks
+    g = golden("blocks.npz")
+    for tag in ("DoubleConv_F.plain", "DoubleConv_F.mid", "DoubleConv_F.res", "Down_FFF", "Up_FFF"):
+        mod = fill_params_(_block_cases(afr)[tag](), salt=tag).cuda().eval()
+        ins = [dev(g[f"{tag}.in{n}"]) for n in range(2) if f"{tag}.in{n}" in g.files]
+        args = ins + ([dev(g["t"])] if tag.startswith(("Down", "Up")) else [])
+        with torch.no_grad():
+            fused = mod(*args)
+            assert afr.last_kernel() in ("fgelu3_tma_kernel", "fgelu3_direct_kernel")
+            blocks.FUSE_GROUPNORM_INFERENCE = False
+            try:
+                unfused = mod(*args)
+            finally:
+                blocks.FUSE_GROUPNORM_INFERENCE = True
+        assert relmax(host(fused), g[f"{tag}.y"]) <= BLOCK_TOL, tag
+        assert relmax(host(fused), host(unfused)) <= 2e-5, tag
+    gu = golden("unet.npz")
+    net = fill_params_(afr.UNet(c_in=3, c_out=3, image_size=16, f_settings=FS, variant=3)).cuda().eval()
+    with torch.no_grad():
+        y = net(dev(gu["v3_s16_c3.x"]), dev(gu["v3_s16_c3.t"]))
+    assert relmax(host(y), gu["v3_s16_c3.y"]) <= UNET_TOL
+
+
+def test_groupnorm1_affine_kernel(afr):
+    torch.manual_seed(2)
+    for shape, dt in [((3, 8, 4, 4), torch.float32), ((5, 32, 32, 32), torch.float32), ((2, 6, 16, 8), torch.bfloat16)]:
+        x = (torch.randn(shape, device="cuda") * 1.7 + 0.4).to(dt)
+        gn = torch.nn.GroupNorm(1, shape[1]).cuda()
+        with torch.no_grad():
+            gn.weight.normal_(1.0, 0.2); gn.bias.normal_(0.0, 0.3)
+            sc, sh = afr.ops.groupnorm1_affine(x, gn.weight, gn.bias, gn.eps)
+            want = gn(x.float())
+            got = x.float() * sc[:, :, None, None] + sh[:, :, None, None]
+        assert relmax(host(got), host(want)) <= 2e-6
+
+
+def test_affine_kernel_vs_oracle(afr, oracle):
+    rng = np.random.default_rng(5)
+    k = oracle.lowpass_taps(np.pi / 2, 3, 2.0)
+    for shape in [(3, 5, 4, 4), (2, 3, 8, 8), (2, 6, 32, 32), (1, 2, 40, 200), (5, 1, 18, 24)]:
+        x, r = (rng.standard_normal(shape).astype(np.float32) for _ in range(2))
+        sc = (1.0 + 0.5 * rng.standard_normal(shape[:2])).astype(np.float32)
+        sh = rng.standard_normal(shape[:2]).astype(np.float32)
+        xhat = x * sc[:, :, None, None] + sh[:, :, None, None]
+        for path in ("auto", "direct"):
+            afr.set_path(path)
+            try:
+                got = afr.ops.filtered_gelu_affine(dev(x), dev(sc), dev(sh), k, k)
+                assert relmax(host(got), oracle.filtered_gelu(xhat, k, k)) <= 1e-5, (shape, path)
+                got = afr.ops.filtered_gelu_affine(dev(x), dev(sc), dev(sh), k, k, residual=dev(r))
+                assert relmax(host(got), oracle.filtered_gelu(xhat + r, k, k)) <= 1e-5, (shape, path)
+            finally:
+                afr.set_path("auto")
+    with pytest.raises(NotImplementedError):
+        afr.ops.filtered_gelu_affine(dev(x), dev(sc), dev(sh), oracle.lowpass_taps(1.0, 6, None), k)
+
+
 def test_param_count_v3(afr):
     # Results.ipynb:121 prints 5896513 for variant 3, c_in=1
     net = afr.UNet(c_in=1, c_out=1, image_size=32, f_settings=FS, variant=3)
