@@ -196,7 +196,7 @@ class _FilteredDown(_TimeConditioned):
         super().__init__()
         self.f_settings = f_settings
         self.jinc_filter = taps_from_settings(f_settings, "down")
-        kw = {"f_settings": f_settings} if self._block is DoubleConv_F else {}
+        kw = {"f_settings": f_settings} if issubclass(self._block, DoubleConv_F) else {}
         self.conv = _pair(self._block, in_channels, out_channels, **kw)
         self._make_emb(emb_dim, out_channels)
 
@@ -211,7 +211,7 @@ class _FilteredUp(_TimeConditioned):
         super().__init__()
         self.f_settings = f_settings
         self.sinc_filter = taps_from_settings(f_settings, "up")
-        kw = {"f_settings": f_settings} if self._block is DoubleConv_F else {}
+        kw = {"f_settings": f_settings} if issubclass(self._block, DoubleConv_F) else {}
         self.conv = _pair(self._block, in_channels, out_channels, in_channels // 2, **kw)
         self._make_emb(emb_dim, out_channels)
 
@@ -238,3 +238,36 @@ class Down_FFF(_FilteredDown):
 class Up_FFF(_FilteredUp):
     """Config D (ddpm_utils.py:389-417)."""
     _block = DoubleConv_F
+
+
+# ---- variant 4 (GroupNorm moved to the 2x grid, between upsample and GELU) ------------------------
+# modules/ddpm_utils.py:145-197, 419-480.  The norm sits between the two resamplers, so the
+# one-kernel fusion does not apply; the block runs as up2x kernel -> nn.GroupNorm -> GELU -> down2x
+# kernel (all with autograd), which keeps the variant available and checkpoint-compatible.
+class DoubleConv_F4(DoubleConv_F):
+    def _act(self, h, norm):
+        h = ops.up2x(h, self.sinc_filter)
+        return ops.down2x(F.gelu(norm(h)), self.jinc_filter)
+
+    def forward(self, x):
+        h = self._act(self.conv1(x), self.norm1)
+        h = self.norm2(self.conv2(h))
+        if self.residual:
+            h = self._act(h + x, self.norm2)            # the reference re-uses norm2 here (:180)
+        return h
+
+
+class Down_F4(_FilteredDown):
+    _block = DoubleConv_F4
+
+    def __init__(self, in_channels, out_channels, emb_dim=256, f_settings=None):
+        super().__init__(in_channels, out_channels, emb_dim, f_settings)
+        self.norm1 = nn.GroupNorm(1, in_channels)       # present (unused) upstream: keeps state_dict keys
+
+
+class Up_F4(_FilteredUp):
+    _block = DoubleConv_F4
+
+    def __init__(self, in_channels, out_channels, emb_dim=256, f_settings=None):
+        super().__init__(in_channels, out_channels, emb_dim, f_settings)
+        self.norm1 = nn.GroupNorm(1, in_channels // 2)

@@ -162,6 +162,18 @@ class _FilteredGelu(torch.autograd.Function):
         return dx, (dx if ctx.has_res else None), None, None
 
 
+def _match_residual(x, residual):
+    """``x + residual`` follows PyTorch type promotion (e.g. bf16 conv output + fp32 skip under
+    autocast -> fp32), like the reference's ``x = x + residual`` (modules/ddpm_utils.py:128)."""
+    residual = _require(residual, "residual")
+    if residual.shape != x.shape:
+        raise ValueError("afr: residual must match x in shape")
+    if residual.dtype != x.dtype:
+        dt = torch.promote_types(x.dtype, residual.dtype)
+        x, residual = x.to(dt), residual.to(dt)
+    return x, residual
+
+
 # ---- public functions -----------------------------------------------------------------
 def up2x(x, filt, out_dtype=None):
     """Zero-stuff x2 + depthwise N x N low-pass, 'same' zero padding, no gain."""
@@ -179,9 +191,7 @@ def filtered_gelu(x, filt_up, filt_down, residual=None):
     Replaces modules/ddpm_utils.py:123-125 / 128-131 / 137-139."""
     x = _require(x)
     if residual is not None:
-        residual = _require(residual, "residual")
-        if residual.shape != x.shape or residual.dtype != x.dtype:
-            raise ValueError("afr: residual must match x in shape and dtype")
+        x, residual = _match_residual(x, residual)
     return _FilteredGelu.apply(x, residual, _taps(filt_up), _taps(filt_down))
 
 
@@ -203,9 +213,7 @@ def filtered_gelu_affine(x, scale, shift, filt_up, filt_down, residual=None):
     if tuple(scale.shape) != (B, C) or tuple(shift.shape) != (B, C) or not scale.is_cuda or not shift.is_cuda:
         raise ValueError("afr: scale and shift must be CUDA tensors of shape [B, C]")
     if residual is not None:
-        residual = _require(residual, "residual")
-        if residual.shape != x.shape or residual.dtype != x.dtype:
-            raise ValueError("afr: residual must match x in shape and dtype")
+        x, residual = _match_residual(x, residual)
     y = torch.empty_like(x)
     with torch.cuda.device(x.device):
         _check(_native.lib().afr_filtered_gelu_affine_fwd(

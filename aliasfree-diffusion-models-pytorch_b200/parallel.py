@@ -42,11 +42,12 @@ class ShardedNoise:
 
 
 def sharded_sample(diffusion, model, n, image_channels, theta=None, seed=0, gather=False,
-                   exact_stream=True, progress=False):
+                   exact_stream=True, progress=False, cuda_graph=False):
     """Batch-sharded Algorithm 1.  Rank r samples images [lo, hi) of the global batch ``n``.
     The start noise is the slice of the seeded CPU draw the unsharded reference would make
     (modules/ddpm_models.py:360).  Returns this rank's ``(x_u8, result_u8)``; with
-    ``gather=True`` rank-ordered full tensors on every rank (equal shard sizes required)."""
+    ``gather=True`` rank-ordered full tensors on every rank (equal shard sizes required).
+    ``cuda_graph=True`` replays one captured reverse step per iteration (per-rank device noise)."""
     rank, ws = world()
     lo, hi = shard_bounds(n, rank, ws)
     g = torch.Generator()
@@ -54,10 +55,14 @@ def sharded_sample(diffusion, model, n, image_channels, theta=None, seed=0, gath
     S = diffusion.img_size
     x0 = torch.randn((n, image_channels, S, S), generator=g)[lo:hi]
     noise = None
-    if exact_stream:
+    if cuda_graph:
+        # the captured step draws its own noise: seed the device generator per rank (distributional,
+        # not bitwise, agreement with an unsharded run)
+        torch.cuda.manual_seed(seed + 1 + rank)
+    elif exact_stream:
         noise = ShardedNoise((n, image_channels, S, S), lo, hi, diffusion.device, seed + 1)
     x, result = diffusion.sample(model, hi - lo, image_channels, theta=theta, x_init=x0,
-                                 noise_source=noise, progress=progress)
+                                 noise_source=noise, progress=progress, cuda_graph=cuda_graph)
     if gather and ws > 1:
         if n % ws:
             raise ValueError("gather=True needs n divisible by the world size")

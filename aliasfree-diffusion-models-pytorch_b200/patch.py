@@ -10,7 +10,8 @@ from . import blocks, ops
 from .diffusion import Diffusion
 
 _FUNCS = ("custom_upsample", "custom_downsample")
-_CLASSES = ("DoubleConv_F", "Down_F", "Up_F", "Down_FF", "Up_FF", "Down_FFF", "Up_FFF")
+_CLASSES = ("DoubleConv_F", "Down_F", "Up_F", "Down_FF", "Up_FF", "Down_FFF", "Up_FFF",
+            "DoubleConv_F4", "Down_F4", "Up_F4")
 _saved = {}
 
 

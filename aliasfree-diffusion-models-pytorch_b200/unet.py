@@ -3,8 +3,8 @@
 The reference UNet is Python glue around the blocks; it is restated here only because the
 GPU box has no copy of the reference to import.  Attribute names (inc, down1, sa1, ...,
 outc, label_emb) and therefore state_dict keys are identical; channel widths follow the
-reference's ``image_size * {1, 2, 4, 8}`` rule.  Variant 4 (GroupNorm at 2x resolution) is
-out of scope.
+reference's ``image_size * {1, 2, 4, 8}`` rule.  Variant 4 (GroupNorm at 2x resolution, an
+upstream experiment) is supported through the standalone resampling kernels (no fusion).
 """
 import torch
 import torch.nn as nn
@@ -17,6 +17,7 @@ _VARIANTS = {
     1: (B.DoubleConv, B.Down_FF, B.Up_FF, True),       # Config B
     2: (B.DoubleConv_F, B.Down_F, B.Up_F, True),       # Config C
     3: (B.DoubleConv_F, B.Down_FFF, B.Up_FFF, True),   # Config D
+    4: (B.DoubleConv_F4, B.Down_F4, B.Up_F4, True),    # experimental upstream: GroupNorm on the 2x grid
 }
 
 
@@ -25,8 +26,6 @@ class UNet(nn.Module):
                  num_classes=None, variant=0):
         super().__init__()
         if variant not in _VARIANTS:
-            if variant == 4:
-                raise NotImplementedError("variant 4 is outside the accelerated path (SURVEY.md section 2)")
             raise ValueError("variant value must be between 0 and 4")
         conv_cls, down_cls, up_cls, filtered = _VARIANTS[variant]
         if filtered and f_settings is None:
@@ -35,7 +34,7 @@ class UNet(nn.Module):
         self.variant = variant
         s = int(image_size)
         stage_kw = {"f_settings": f_settings} if filtered else {}
-        conv_kw = {"f_settings": f_settings} if conv_cls is B.DoubleConv_F else {}
+        conv_kw = {"f_settings": f_settings} if issubclass(conv_cls, B.DoubleConv_F) else {}
 
         self.inc = conv_cls(c_in, s, **conv_kw)
         self.down1 = down_cls(s, 2 * s, **stage_kw)

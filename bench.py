@@ -314,8 +314,17 @@ def ddpm_v3(afr, ws, rank, global_batch, steps, warmup):
             ms, mode = g_ms, "cuda_graph"
     except Exception as e:                 # capture is an optimisation, never a requirement
         mode = "eager (graph capture failed: %s)" % repr(e)[:120]
+    bf16_ms = None
+    try:                                   # extra data point, not the headline: same step under bf16 autocast
+        def bf16_step():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                diff._reverse_step(net, x, 500, torch.randn_like(x))
+        bf16_total, _ = timed_loop(bf16_step, steps, warmup, ws)
+        bf16_ms = bf16_total / steps
+    except Exception:
+        pass
     return {"samples_per_sec": global_batch / (999 * ms / 1e3), "ms_per_reverse_step": ms, "mode": mode,
-            "eager_ms_per_reverse_step": eager_ms,
+            "eager_ms_per_reverse_step": eager_ms, "bf16_autocast_ms_per_reverse_step": bf16_ms,
             "global_batch": global_batch, "per_rank_batch": n, "steps_timed": steps,
             "note": "random-init UNet variant=3 c=3 32x32, fp32 (PyTorch default TF32 conv); "
                     "samples/sec = batch / (999 x measured ms per reverse step); strong scaling over ranks",

@@ -143,12 +143,15 @@ def gen_blocks(utils):
     run("Up_F", utils.Up_F(16, 8, f_settings=fs), x4, sk)
     run("Up_FF", utils.Up_FF(16, 8, f_settings=fs), x4, sk)
     run("Up_FFF", utils.Up_FFF(16, 8, f_settings=fs), x4, sk)
+    run("DoubleConv_F4.res", utils.DoubleConv_F4(8, 8, residual=True, f_settings=fs), x8)
+    run("Down_F4", utils.Down_F4(8, 16, f_settings=fs), x8)
+    run("Up_F4", utils.Up_F4(16, 8, f_settings=fs), x4, sk)
     np.savez_compressed(os.path.join(HERE, "blocks.npz"), **out)
 
 
 def gen_unet(models):
     out = {}
-    for variant, size, c in [(1, 16, 3), (2, 16, 3), (3, 16, 3), (3, 32, 1)]:
+    for variant, size, c in [(1, 16, 3), (2, 16, 3), (3, 16, 3), (3, 32, 1), (4, 16, 3)]:
         tag = f"v{variant}_s{size}_c{c}"
         net = models.UNet(c_in=c, c_out=c, image_size=size, device="cpu",
                           f_settings=F_SETTINGS, variant=variant)

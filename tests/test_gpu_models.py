@@ -43,11 +43,15 @@ def _block_cases(afr):
         "Up_F": lambda: afr.Up_F(16, 8, f_settings=FS),
         "Up_FF": lambda: afr.Up_FF(16, 8, f_settings=FS),
         "Up_FFF": lambda: afr.Up_FFF(16, 8, f_settings=FS),
+        "DoubleConv_F4.res": lambda: afr.DoubleConv_F4(8, 8, residual=True, f_settings=FS),
+        "Down_F4": lambda: afr.Down_F4(8, 16, f_settings=FS),
+        "Up_F4": lambda: afr.Up_F4(16, 8, f_settings=FS),
     }
 
 
 @pytest.mark.parametrize("tag", ["DoubleConv_F.plain", "DoubleConv_F.mid", "DoubleConv_F.res", "Down_F",
-                                 "Down_FF", "Down_FFF", "Up_F", "Up_FF", "Up_FFF"])
+                                 "Down_FF", "Down_FFF", "Up_F", "Up_FF", "Up_FFF", "DoubleConv_F4.res",
+                                 "Down_F4", "Up_F4"])
 def test_blocks_match_reference(afr, tag):
     g = golden("blocks.npz")
     mod = fill_params_(_block_cases(afr)[tag](), salt=tag).cuda()
@@ -61,7 +65,7 @@ def test_blocks_match_reference(afr, tag):
     assert not any("filter" in k for k in mod.state_dict())
 
 
-@pytest.mark.parametrize("variant,size,c", [(1, 16, 3), (2, 16, 3), (3, 16, 3), (3, 32, 1)])
+@pytest.mark.parametrize("variant,size,c", [(1, 16, 3), (2, 16, 3), (3, 16, 3), (3, 32, 1), (4, 16, 3)])
 def test_unet_matches_reference(afr, variant, size, c):
     g = golden("unet.npz")
     tag = f"v{variant}_s{size}_c{c}"

@@ -94,6 +94,8 @@ def test_state_dict_keys_match_reference_layout(afr):
         afr.UNet(variant=3)                     # f_settings missing, like the reference
     with pytest.raises(ValueError):
         afr.UNet(variant=7)
+    n4 = afr.UNet(c_in=3, c_out=3, image_size=32, f_settings=FS, variant=4)
+    assert sum(p.numel() for p in n4.parameters()) == 5898051      # variant 4 count
 
 
 def test_state_dict_is_strictly_loadable_from_reference():
@@ -106,7 +108,7 @@ def test_state_dict_is_strictly_loadable_from_reference():
     sys.path.insert(0, "/root/reference")
     import modules.ddpm_models as rm
     import aliasfree_b200 as afr
-    for v in (0, 1, 2, 3):
+    for v in (0, 1, 2, 3, 4):
         ref = rm.UNet(c_in=3, c_out=3, image_size=16, device="cpu", f_settings=FS, variant=v)
         ours = afr.UNet(c_in=3, c_out=3, image_size=16, f_settings=FS, variant=v)
         ours.load_state_dict(ref.state_dict(), strict=True)
