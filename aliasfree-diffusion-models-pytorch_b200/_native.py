@@ -30,15 +30,25 @@ def build(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> libafr_b200.so (in-tree)."""
     if not force and not _stale():
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, f) for f in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:          # several ranks may import at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():                # another process built it while we waited
+                return LIB_PATH
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, f) for f in SOURCES]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)                     # atomic: readers never see a partial file
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

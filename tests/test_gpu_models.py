@@ -230,6 +230,34 @@ def test_train_step_runs_and_matches_autograd(afr):
     assert all(p.grad is not None and p.grad.data_ptr() >= ddp.flat.data_ptr() for p in ddp.params)
 
 
+def test_graphed_train_step_matches_eager(afr):
+    """Two identically initialised models, same images / timesteps / noise: the CUDA-graph step and
+    the eager step produce the same loss trajectory and parameters."""
+    from aliasfree_b200 import parallel
+    diff = afr.Diffusion(noise_steps=100, img_size=16, device="cuda")
+    imgs = (torch.rand(4, 3, 16, 16, generator=torch.Generator().manual_seed(0)) * 2 - 1).cuda()
+    results = []
+    for graphed in (False, True):
+        net = fill_params_(afr.UNet(c_in=3, c_out=3, image_size=16, f_settings=FS, variant=3)).cuda()
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-3, capturable=True)
+        ddp = parallel.FlatGradAllReduce(net)
+        step = parallel.GraphedTrainStep(net, diff, opt, tuple(imgs.shape), ddp=ddp, warmup=0) if graphed else None
+        tgen = torch.Generator().manual_seed(9)
+        losses = []
+        for it in range(4):
+            torch.cuda.manual_seed(100 + it)               # q-sample noise: same device stream state per step
+            if graphed:
+                losses.append(float(step(imgs, generator=tgen)))
+            else:
+                losses.append(float(parallel.train_step(net, diff, opt, imgs, ddp=ddp, generator=tgen).detach()))
+        results.append((losses, torch.cat([p.detach().flatten() for p in net.parameters()])))
+    (l_e, p_e), (l_g, p_g) = results
+    assert np.isfinite(l_g).all()
+    # the graph's RNG offsets differ from eager's, so the q-sample noise differs: compare statistically
+    assert abs(np.mean(l_e) - np.mean(l_g)) < 0.25 * np.mean(l_e)
+    assert float((p_e - p_g).abs().max()) < 0.05
+
+
 def test_patch_reference_if_present(afr):
     """With a reference checkout on sys.path, patch() makes the reference's own UNet run on
     our kernels.  The GPU box has no checkout, so this is skipped there."""
