@@ -1,9 +1,10 @@
 """The reference's resampling path restated with the same PyTorch calls it makes
 (modules/filtrs.py:71-94, modules/ddpm_utils.py:123-125): zero-stuff + depthwise F.conv2d
-('same' padding, groups=C) + strided slice + F.gelu.  TEST / BENCH INFRASTRUCTURE ONLY, like
-everything under oracle/: it is what the upstream code executes when run in eager mode on a
-GPU, i.e. the "kernel to beat" on the B200 (the reference itself cannot travel to the GPU box).
-Pinned by tests/test_oracle.py against the same golden fixtures as the C oracle."""
+('same' padding, groups=C) + strided slice + F.gelu.  BASELINE / TEST INFRASTRUCTURE ONLY (never imported by the product package): it is
+what the upstream code executes when run in eager mode on a GPU, i.e. the "kernel to beat" on the
+B200 (the reference itself cannot travel to the GPU box; it has no setup.py, so there is nothing to
+pip-install into baseline/_ref).  Pinned by tests/test_oracle.py against the same golden fixtures
+as the C oracle."""
 import torch
 import torch.nn.functional as F
 

@@ -76,6 +76,7 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower(), f
+                assert "import baseline" not in src and "from baseline" not in src, f
 
 
 def test_state_dict_keys_match_reference_layout(afr):

@@ -96,9 +96,9 @@ def test_empty_and_shapes(oracle):
 
 
 def test_torch_restatement_matches_reference():
-    """oracle/torch_restatement.py (used by bench.py as the eager-GPU baseline) on CPU vs the goldens."""
+    """baseline/torch_eager_reference.py (used by bench.py as the eager-GPU baseline) on CPU vs the goldens."""
     import torch
-    from oracle import torch_restatement as tr
+    from baseline import torch_eager_reference as tr
     g = golden("resample.npz")
     for name in _cases():
         x = torch.from_numpy(g[f"{name}.x"]); ku = torch.from_numpy(g[f"{name}.ku"]); kd = torch.from_numpy(g[f"{name}.kd"])
