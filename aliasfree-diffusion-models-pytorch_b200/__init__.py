@@ -14,6 +14,7 @@ from .diffusion import Diffusion
 from .patch import patch, unpatch
 from . import parallel
 from .tasks import rotation_results, shift_results
+from .hostio import HostPipeline
 
 build = _native.build
 set_path = _native.set_path
@@ -24,5 +25,5 @@ __all__ = ["circularLowpassKernel", "taps_from_settings", "Taps", "custom_upsamp
            "custom_downsample", "up2x", "down2x", "filtered_gelu", "rotate", "ddpm_update_",
            "DoubleConv", "DoubleConv_F", "DoubleConv_F4", "Down", "Down_F", "Down_F4", "Down_FF", "Down_FFF",
            "Up", "Up_F", "Up_F4",
-           "Up_FF", "Up_FFF", "SelfAttention", "UNet", "Diffusion", "patch", "unpatch", "parallel", "rotation_results", "shift_results",
+           "Up_FF", "Up_FFF", "SelfAttention", "UNet", "Diffusion", "patch", "unpatch", "parallel", "rotation_results", "shift_results", "HostPipeline",
            "build", "set_path", "last_kernel", "launch_count"]

@@ -93,9 +93,9 @@ def _down_bwd(dy, k, H, W):
     return dv
 
 
-def _fgelu_fwd(x, res, ku, kd):
+def _fgelu_fwd(x, res, ku, kd, out=None):
     B, C, H, W = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
     with torch.cuda.device(x.device):
         _check(_native.lib().afr_filtered_gelu_fwd(
             x.data_ptr(), None if res is None else res.data_ptr(), y.data_ptr(), B, C, H, W,

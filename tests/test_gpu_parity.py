@@ -311,3 +311,15 @@ def test_streaming_kernel_partial_tiles(afr, oracle, shape):
             assert relmax(host(yb), oracle.filtered_gelu(host(xb), ku, kd)) <= BF16_TOL
     finally:
         afr.set_path("auto")
+
+
+def test_host_pipeline(afr, oracle):
+    """Pinned host tensor in, pinned host tensor out, chunked over three streams (ragged last chunk)."""
+    k = oracle.lowpass_taps(np.pi / 2, 3, 2.0)
+    x = torch.randn(11, 6, 16, 16).pin_memory()
+    y = torch.empty_like(x).pin_memory()
+    pipe = afr.HostPipeline((4, 6, 16, 16))
+    for _ in range(2):                                   # second call reuses slots/streams
+        pipe.filtered_gelu(x, y, k, k)
+        torch.cuda.synchronize()
+        assert relmax(y.numpy(), oracle.filtered_gelu(x.numpy(), k, k)) <= FP32_TOL
