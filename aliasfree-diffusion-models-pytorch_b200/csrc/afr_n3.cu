@@ -325,6 +325,13 @@ fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T
                                  make_affine(kAff ? scale : nullptr, shift, p, true, j, W)};
     GlobalRows<T, false> sd{kBwd ? dy + base : nullptr, nullptr, H, W, j, Affine{0.f, 0.f, 0.f, 0.f}};
     const bool own0 = (s > 0) && ((threadIdx.x & 31) == 0);
+    // all rows this thread will walk are requested up front (L1 prefetch), so the row-by-row loads
+    // of the step loop do not each expose a full memory latency
+    for (int r = max(i0 - 1, 0); r <= min(i0 + R, H - 1); ++r) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(x + base + (long)r * W));
+        if (kRes) asm volatile("prefetch.global.L1 [%0];" ::"l"(res + base + (long)r * W));
+        if (kBwd) asm volatile("prefetch.global.L1 [%0];" ::"l"(dy + base + (long)r * W));
+    }
     strip_core<kBwd>(sx, sd, out + base, W, i0, i1, R, valid, j == 0, own0, kU, kG, kB);
 }
 

@@ -123,6 +123,17 @@ def max_over_ranks(v, ws):
     return float(t.item())
 
 
+def all_ok(flag, ws):
+    """Collective AND: optional paths (graph capture ...) are taken only if EVERY rank can take them,
+    so that the barriers inside timed_loop stay matched across ranks."""
+    if ws == 1:
+        return bool(flag)
+    import torch.distributed as dist
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
 def timed_loop(fn, steps, warmup, ws, per_step_events=False):
     """W untimed steps, then exactly K timed steps bracketed by barrier + synchronize.
     Returns (total_ms max over ranks, [per-step ms] on this rank)."""
@@ -305,24 +316,32 @@ def ddpm_v3(afr, ws, rank, global_batch, steps, warmup):
     eager_ms /= steps
     launches = (afr.launch_count() - l0) // (steps + warmup)
     ms, mode = eager_ms, "eager"
+    graph = None
     try:                                   # one reverse step captured in a CUDA graph and replayed
         graph, step_dev = diff.capture_reverse_step(net, x)
         step_dev.fill_(900)
+    except Exception as e:                 # capture is an optimisation, never a requirement
+        mode = "eager (graph capture failed: %s)" % repr(e)[:120]
+        graph = None
+    if all_ok(graph is not None, ws):
         g_ms, _ = timed_loop(graph.replay, steps, warmup, ws)
         g_ms /= steps
         if g_ms < ms:
             ms, mode = g_ms, "cuda_graph"
-    except Exception as e:                 # capture is an optimisation, never a requirement
-        mode = "eager (graph capture failed: %s)" % repr(e)[:120]
     bf16_ms = None
-    try:                                   # extra data point, not the headline: same step under bf16 autocast
-        def bf16_step():
-            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-                diff._reverse_step(net, x, 500, torch.randn_like(x))
+
+    def bf16_step():                       # extra data point, not the headline: same step under bf16 autocast
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            diff._reverse_step(net, x, 500, torch.randn_like(x))
+
+    try:
+        bf16_step()
+        bf16_ok = True
+    except Exception:
+        bf16_ok = False
+    if all_ok(bf16_ok, ws):
         bf16_total, _ = timed_loop(bf16_step, steps, warmup, ws)
         bf16_ms = bf16_total / steps
-    except Exception:
-        pass
     return {"samples_per_sec": global_batch / (999 * ms / 1e3), "ms_per_reverse_step": ms, "mode": mode,
             "eager_ms_per_reverse_step": eager_ms, "bf16_autocast_ms_per_reverse_step": bf16_ms,
             "global_batch": global_batch, "per_rank_batch": n, "steps_timed": steps,
@@ -376,18 +395,20 @@ def train_v3(afr, ws, rank, global_batch, steps, warmup):
     launches = (afr.launch_count() - l0) // (steps + warmup)
     eager_ms = total_ms / steps
     ms, mode = eager_ms, "eager"
+    gstep = None
     try:                                   # same step, device work replayed from two CUDA graphs
         opt_g = torch.optim.AdamW(net.parameters(), lr=3e-4, capturable=True)
         gstep = parallel.GraphedTrainStep(net, diff, opt_g, tuple(dev.shape), ddp=ddp)
-
+    except Exception as e:
+        mode = "eager (graph capture failed: %s)" % repr(e)[:160]
+        gstep = None
+    if all_ok(gstep is not None, ws):
         def graphed():
             losses.append(gstep(host))
 
         g_total, _ = timed_loop(graphed, steps, warmup, ws)
         if g_total / steps < ms:
             ms, mode = g_total / steps, "cuda_graph"
-    except Exception as e:
-        mode = "eager (graph capture failed: %s)" % repr(e)[:160]
     return {"images_per_sec": global_batch / (ms / 1e3), "ms_per_step": ms, "mode": mode, "eager_ms_per_step": eager_ms,
             "global_batch": global_batch, "per_rank_batch": hi - lo, "steps_timed": steps,
             "final_loss": float(losses[-1].item()), "afr_launches_per_step": int(launches),
