@@ -6,8 +6,10 @@
 //
 //   per output row i the thread needs "mid" rows 2i-1, 2i, 2i+1 at columns 2j-1 .. 2j+7;
 //   row 2i+1 of this iteration is row 2(i+1)-1 of the next, so it is carried and only two
-//   new mid rows (18 GELUs for 4 outputs) are evaluated per step -- 4.5 per output against
-//   the ideal 4.  x rows are carried the same way (one new row of 6 values per step).
+//   new mid rows are evaluated per step; their column 2j-1 is the left neighbour's column
+//   2j+7 and arrives by warp shuffle, so a step costs 16 GELUs for 4 outputs -- the ideal 4
+//   per output.  x rows are carried the same way (one new row of 6 values per step), and
+//   GELUs are evaluated in pairs on packed f32x2 FMAs (afr_common.cuh).
 //
 // Forward:  mid = gelu(up(x; kU)),                      out = down(mid; kB), kB = k_down
 // Adjoint:  mid = gelu'(up(x; kU)) * up(dy; kG),        out = down(mid; kB),
@@ -17,8 +19,8 @@
 // 2i-1 at i == 0 can fall outside, which is what `first_col` / the i0 == 0 start handle.
 //
 // Two data paths feed the same core:
-//   direct  rows are read from global memory (128-bit loads + two scalars, L1-cached),
-//           used for tiny planes (4x4, 8x8) and shapes TMA cannot describe;
+//   direct  rows are read from global memory (128-bit loads + two scalars, L1-prefetched),
+//           used for 4x4 planes and shapes TMA cannot describe;
 //   tma     row-streaming: a CTA owns P planes x one column tile for the whole plane height; one
 //           elected thread keeps a 2-stage ring of cp.async.bulk.tensor boxes
 //           [Tw + 2*halo, R+1 rows, P planes] in flight (out-of-bounds zero fill = the conv's
