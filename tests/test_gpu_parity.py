@@ -323,3 +323,21 @@ def test_host_pipeline(afr, oracle):
         pipe.filtered_gelu(x, y, k, k)
         torch.cuda.synchronize()
         assert relmax(y.numpy(), oracle.filtered_gelu(x.numpy(), k, k)) <= FP32_TOL
+
+
+def test_misaligned_base_pointer_falls_back(afr, oracle):
+    """A tensor whose storage offset breaks the 16-byte alignment cannot use TMA or 128-bit loads:
+    the call must still succeed (generic kernels) and be correct, forward and backward."""
+    k = oracle.lowpass_taps(np.pi / 2, 3, 2.0)
+    flat = torch.randn(2 * 3 * 16 * 16 + 1, device="cuda")
+    x = flat[1:].view(2, 3, 16, 16)                       # contiguous, but 4-byte aligned only
+    assert x.is_contiguous() and x.data_ptr() % 16 != 0
+    xg = x.detach().requires_grad_(True)
+    y = afr.filtered_gelu(xg, k, k)
+    assert afr.last_kernel() == "fgelu_generic_kernel"
+    assert relmax(host(y), oracle.filtered_gelu(host(x), k, k)) <= FP32_TOL
+    dy = torch.randn_like(y)
+    (dx,) = torch.autograd.grad(y, xg, dy)
+    assert relmax(host(dx), oracle.filtered_gelu_bwd(host(x), host(dy), k, k)) <= FP32_TOL
+    assert relmax(host(afr.up2x(x, k)), oracle.up2x(host(x), k)) <= FP32_TOL
+    assert relmax(host(afr.down2x(x, k)), oracle.down2x(host(x), k)) <= FP32_TOL
