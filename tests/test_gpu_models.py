@@ -281,3 +281,24 @@ def test_patch_reference_if_present(afr):
     finally:
         afr.unpatch()
     assert rm.DoubleConv_F is not afr.DoubleConv_F
+
+
+def test_full_schedule_and_rotation_sweep(afr):
+    """The full T=1000 Algorithm-1 schedule (graph replay) stays finite and returns the reference's
+    output structure; the Config-E driver deals frames and re-seeds per frame."""
+    net = fill_params_(afr.UNet(c_in=3, c_out=3, image_size=16, f_settings=FS, variant=3)).cuda()
+    diff = afr.Diffusion(noise_steps=1000, img_size=16, device="cuda")
+    x_u8, res_u8 = diff.sample(net, 2, 3, cuda_graph=True)
+    assert x_u8.dtype == torch.uint8 and tuple(x_u8.shape) == (2, 3, 16, 16)
+    assert tuple(res_u8.shape) == (2 * 10, 3, 16, 16)          # snapshots at i = 900..100 (9) + final
+    xf, _ = diff.sample(net, 2, 3, cuda_graph=True, return_float=True)
+    assert torch.isfinite(xf).all()
+    short = afr.Diffusion(noise_steps=6, img_size=16, device="cuda")
+    thetas = np.linspace(-90, 90, 3)
+    xs, results = afr.rotation_results(net, short, thetas, n=2, image_channels=3, seed=42)
+    assert len(xs) == 3 and all(x is not None and tuple(x.shape) == (2, 3, 16, 16) for x in xs)
+    xs2, _ = afr.rotation_results(net, short, thetas, n=2, image_channels=3, seed=42)
+    assert all(torch.equal(a, b) for a, b in zip(xs, xs2))      # same seed per frame -> repeatable
+    assert not torch.equal(xs[0], xs[2])                        # different angles -> different frames
+    sh = afr.shift_results(net, short, np.array([0, 3]), n=2, image_channels=3, seed=42)
+    assert len(sh) == 2 and sh[0].dtype == torch.uint8
