@@ -12,7 +12,8 @@ dt = torch.bfloat16 if (len(sys.argv) > 6 and sys.argv[6] == "bf16") else torch.
 path = sys.argv[7] if len(sys.argv) > 7 else "auto"
 reps = int(sys.argv[8]) if len(sys.argv) > 8 else 5
 afr.set_path(path)
-k = afr.Taps(afr.circularLowpassKernel(np.pi / 2, 3, 2))
+NTAPS = int(os.environ.get("AFR_CASE_N", "3"))
+k = afr.Taps(afr.circularLowpassKernel(np.pi / 2, NTAPS, 2))
 x = torch.randn(B, C, H, W, device="cuda").to(dt)
 dy = torch.randn_like(x); r = torch.randn_like(x)
 big = torch.randn(B, C, 2 * H, 2 * W, device="cuda").to(dt) if op == "up_bwd" else None
