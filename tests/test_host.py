@@ -236,3 +236,14 @@ def test_two_rank_gloo_data_parallel(tmp_path):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_shift_matches_scipy_grid_wrap(afr):
+    """Diffusion.shift_2d_matrix (torch.roll) == scipy.ndimage.shift(..., mode='grid-wrap') for the
+    integer shifts the reference uses (modules/ddpm_models.py:431-436)."""
+    from scipy import ndimage
+    x = torch.randn(2, 3, 8, 10)
+    for h, v in [(1, 0), (-1, 0), (3, -2), (0, 5)]:
+        want = ndimage.shift(input=x.numpy(), shift=(0, 0, v, h), mode="grid-wrap")
+        got = afr.Diffusion.shift_2d_matrix(x, h, v, "cpu").numpy()
+        np.testing.assert_allclose(got, want, atol=2e-6)
