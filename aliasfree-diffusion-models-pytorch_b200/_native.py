@@ -94,6 +94,10 @@ def lib():
         with _lock:
             if _lib is None:
                 import torch  # noqa: F401  (maps libcudart.so.12)
+                alt = os.environ.get("AFR_LIB_PATH")          # tuning builds (tools/), never set in production
+                if alt:
+                    _lib = _declare(ctypes.CDLL(alt, mode=ctypes.RTLD_GLOBAL))
+                    return _lib
                 if _stale():
                     build()
                 _lib = _declare(ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL))

@@ -407,8 +407,11 @@ struct TileCfg {
 // mid row and input row simply stay in registers across chunks, so there is no per-segment
 // start-up work at all, and the next two chunks are always in flight (2-stage TMA/mbarrier
 // ring) while the current one is being computed.
+#ifndef AFR_TMA_MINB
+#define AFR_TMA_MINB 1
+#endif
 template <typename T, bool kBwd, bool kRes, bool kAff>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, AFR_TMA_MINB)
 fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mres,
                   const __grid_constant__ CUtensorMap mdy, const float *__restrict__ scale,
                   const float *__restrict__ shift, T *__restrict__ out, long planes, int H,
