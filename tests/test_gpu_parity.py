@@ -126,7 +126,8 @@ def test_oracle_fp32(afr, oracle, shape):
             afr.set_path("auto")
 
 
-@pytest.mark.parametrize("shape", [(2, 4, 32, 32), (1, 2, 64, 64), (9, 3, 4, 4), (2, 2, 16, 24), (1, 2, 9, 7)])
+@pytest.mark.parametrize("shape", [(2, 4, 32, 32), (1, 2, 64, 64), (9, 3, 4, 4), (2, 2, 16, 24), (1, 2, 9, 7),
+                                   (3, 2, 10, 12), (2, 1, 6, 20), (1, 3, 24, 136)])
 @pytest.mark.parametrize("n", [3, 6])
 def test_oracle_bf16(afr, oracle, shape, n):
     rng = np.random.default_rng(7)
