@@ -246,13 +246,15 @@ def reference_eager_gpu(afr):
 
 
 # ---- sweep over the other ops / shapes / dtypes (reported, not the headline) ------------------
-def sweep(afr, quick):
+def sweep(afr, quick, grid=False):
     k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
     k6 = afr.circularLowpassKernel(np.pi / 2, 6, 2)
     shapes = [(256, 128, 64, 64), (1024, 64, 32, 32), (16, 64, 256, 256), (128, 512, 32, 32),
               (4096, 256, 4, 4), (4096, 128, 8, 8), (4096, 64, 16, 16), (2048, 32, 32, 32)]
     if quick:
         shapes = shapes[:2] + shapes[4:5]
+    if grid:    # the whole BASELINE configs[4] grid: C in {64..512} x H=W in {32..256}, input = 256 MiB fp32
+        shapes = [(max(1, (1 << 26) // (C * HW * HW)), C, HW, HW) for C in (64, 128, 256, 512) for HW in (32, 64, 128, 256)]
     rows = []
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")   # 256 MiB > L2
 
@@ -444,6 +446,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--full-sweep", action="store_true")
+    ap.add_argument("--grid-sweep", action="store_true", help="sweep = the full BASELINE configs[4] C x HW grid")
     ap.add_argument("--no-ddpm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ddpm-batch", type=int, default=4096)
@@ -545,7 +548,7 @@ def main():
             out["reference_eager_gpu"] = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
         try:
-            out["sweep"] = sweep(afr, quick=not args.full_sweep)
+            out["sweep"] = sweep(afr, quick=not args.full_sweep, grid=args.grid_sweep)
         except Exception as e:                      # never lose the headline to a side table
             out["sweep"] = {"error": repr(e)[:300]}
     if not args.no_ddpm:
