@@ -104,7 +104,7 @@ def lib():
     return _lib
 
 
-PATHS = {"auto": 0, "direct": 1, "tma": 2, "generic": 3}
+PATHS = {"auto": 0, "direct": 1, "tma": 2, "generic": 3, "direct_general": 4, "tma_general": 5}
 
 
 def set_path(name):

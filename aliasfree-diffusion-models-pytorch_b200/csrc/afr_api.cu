@@ -38,6 +38,8 @@ int current_path()
             if (!strcmp(e, "direct")) p = AFR_PATH_DIRECT;
             else if (!strcmp(e, "tma")) p = AFR_PATH_TMA;
             else if (!strcmp(e, "generic")) p = AFR_PATH_GENERIC;
+            else if (!strcmp(e, "direct_general")) p = AFR_PATH_DIRECT_GENERAL;
+            else if (!strcmp(e, "tma_general")) p = AFR_PATH_TMA_GENERAL;
         }
         g_path.store(p);
     }
@@ -134,7 +136,7 @@ const char *afr_status_string(int s)
 int afr_set_path(int path)
 {
     int old = current_path();
-    if (path >= AFR_PATH_AUTO && path <= AFR_PATH_GENERIC) g_path.store(path);
+    if (path >= AFR_PATH_AUTO && path <= AFR_PATH_TMA_GENERAL) g_path.store(path);
     return old;
 }
 
@@ -250,7 +252,11 @@ static int fused_common(const void *x, const void *residual, const void *dy, voi
         return fail(AFR_ERR_MISALIGNED, "misaligned buffer");
     cudaStream_t s = (cudaStream_t)stream;
     begin_call();
-    const int path = current_path();
+    int path = current_path();
+    // *_GENERAL: same kernel family with the symmetric-tap fast path switched off (tests, A/B timing)
+    const bool allow_sym = (path != AFR_PATH_DIRECT_GENERAL && path != AFR_PATH_TMA_GENERAL);
+    if (path == AFR_PATH_DIRECT_GENERAL) path = AFR_PATH_DIRECT;
+    if (path == AFR_PATH_TMA_GENERAL) path = AFR_PATH_TMA;
     const void *ptrs[4] = {x, residual, bwd ? dy : nullptr, out};
     if (N_up == 3 && N_down == 3 && path != AFR_PATH_GENERIC && n3_fgelu_supported(H, W, ptrs, 4, dtype)) {
         const bool tma_ok = n3_fgelu_tma_supported(planes, H, W, ptrs, 4, dtype, 1 + (residual ? 1 : 0) + (bwd ? 1 : 0));
@@ -264,7 +270,7 @@ static int fused_common(const void *x, const void *residual, const void *dy, voi
         set_taps3(kG, taps_down, true);
         set_taps3(kB, bwd ? taps_up : taps_down, bwd);
         return cuda_status(n3_fgelu(x, residual, dy, scale, shift, out, planes, H, W, kU, kG, kB, bwd, dtype,
-                                    use_tma, s, &g_last_kernel),
+                                    use_tma, allow_sym, s, &g_last_kernel),
                            "fgelu3 kernel");
     }
     if (scale)

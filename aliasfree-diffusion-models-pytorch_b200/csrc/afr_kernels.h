@@ -25,7 +25,7 @@ bool n3_fgelu_tma_supported(long planes, int H, int W, const void *const *ptrs, 
                             int n_inputs);
 cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, const float *scale, const float *shift,
                      void *out, long planes, int H, int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB,
-                     bool bwd, int dtype, bool use_tma, cudaStream_t s, const char **kernel_name);
+                     bool bwd, int dtype, bool use_tma, bool allow_sym, cudaStream_t s, const char **kernel_name);
 // up-like with N==3: in [planes,H,W] -> out [planes,2H,2W]
 bool n3_up_supported(int H, int W, const void *in, const void *out, int in_dtype, int out_dtype);
 cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,

@@ -180,8 +180,17 @@ __device__ __forceinline__ Affine make_affine(const float *scale, const float *s
 // ---------------------------------------------------------------------------------
 // the strip core
 // ---------------------------------------------------------------------------------
-// One output row.  In: xa/da = input rows i (x / dy), mp = mid row 2i-1.  Loads rows i+1 into
-// xb/db, evaluates mid rows 2i (local) and 2i+1 (-> mo), stores out[i][j..j+3] if `store`.
+// Per-thread state carried from one output row to the next.  Two sets are used ping-pong so that
+// "row i+1 becomes row i" costs no moves; members a variant does not touch never become registers.
+struct RowSet {
+    float x[6], d[6];      // input row (x / dy), columns j-1 .. j+4
+    float m[9];            // general taps: mid row 2i-1, columns 2j-1 .. 2j+7
+    float hx[5], hd[5];    // symmetric taps: x[c] + x[c+1] (and dy likewise), c = 1..4 used
+    float r[4];            // symmetric taps: contribution of mid row 2i-1 to the 4 outputs
+};
+
+// One output row, general 3x3 taps.  In: A.x / A.d = input rows i, A.m = mid row 2i-1.  Loads rows
+// i+1 into B.x / B.d, evaluates mid rows 2i (local) and 2i+1 (-> B.m), stores out[i][j..j+3] if `store`.
 //
 // Column 0 of every mid row (X = 2j-1) is the same sample as column 8 of the thread one strip to
 // the left, so it is fetched from lane-1 with a shuffle instead of being recomputed: 16 GELUs per
@@ -189,13 +198,18 @@ __device__ __forceinline__ Affine make_affine(const float *scale, const float *s
 // run on safe coordinates with `store` off).  `own0` marks the lanes whose left neighbour is not
 // lane-1 (first strip of a later column tile, or lane 0 when the strip count does not divide 32);
 // they compute column 0 themselves in a short divergent branch.
+struct StepK {             // general-tap kernels
+    Taps3 kU, kG, kB;
+};
+
 template <bool kBwd, class SX, class SD, typename TO>
 __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__restrict__ out, int W, int i,
-                                           bool store, bool first_col, bool own0, const Taps3 &kU,
-                                           const Taps3 &kG, const Taps3 &kB, const float (&xa)[6],
-                                           float (&xb)[6], const float (&da)[6], float (&db)[6],
-                                           const float (&mp)[9], float (&mo)[9])
+                                           bool store, bool first_col, bool own0, const StepK &K,
+                                           const RowSet &A, RowSet &B)
 {
+    const Taps3 &kU = K.kU, &kG = K.kG, &kB = K.kB;
+    const float (&xa)[6] = A.x, (&da)[6] = A.d, (&mp)[9] = A.m;
+    float (&xb)[6] = B.x, (&db)[6] = B.d, (&mo)[9] = B.m;
     sx.load(i + 1, xb);
     if (kBwd) sd.load(i + 1, db);
     float me[9];
@@ -245,72 +259,189 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
     if (store) st4(out + (long)i * W, make_float4(o[0], o[1], o[2], o[3]));
 }
 
-// R steps starting at row i0 (R is warp-uniform); rows >= i1 are computed but not stored.
-template <bool kBwd, class SX, class SD, typename TO>
-__device__ __forceinline__ void strip_core(const SX &sx, const SD &sd, TO *__restrict__ out, int W,
-                                           int i0, int i1, int R, bool valid, bool first_col, bool own0,
-                                           const Taps3 &kU, const Taps3 &kG, const Taps3 &kB)
+// The same step for D4-symmetric taps [[a,b,a],[b',c,b'],[a,b,a]] (every filter circularLowpassKernel
+// designs, modules/filtrs.py:20-37: a radial profile times an outer product of a symmetric window).
+// Each of the four polyphase classes of the 2x grid then carries ONE tap value s_ph, so
+//   u = s_ph * xi,  xi = x | x+x_right | x+x_below | sum of the 2x2 block          (adds only)
+// and the multiplications move out of the stencil:
+//   forward  gelu(s*xi) = s * ghat_ph(xi),  ghat_ph(xi) = relu(xi) - |xi| 2^P(s|xi|)   (s >= 0):
+//            P(s t) is a polynomial in t with per-phase coefficients p_k s^k (host), and the factor s
+//            is folded into the down taps (every down tap reads exactly one phase class);
+//   adjoint  dg = sG_ph * delta (delta = the same sums of dy) with sG folded into the down taps,
+//            w = (kappa s_ph) * xi feeds the unchanged derivative.
+// With top/bottom-symmetric down taps the odd mid row 2i+1 contributes the same 3-tap sum r[q] to
+// output rows i and i+1, so r is what is carried (4 registers instead of a 9-value mid row) and an
+// output costs 7 FMA-pipe operations instead of 9.  Per output row a thread issues 12 + 28 FMA-pipe
+// operations around the 16 GELUs instead of 36 + 36.
+enum { PH_EE = 0, PH_EO = 1, PH_OE = 2, PH_OO = 3 };   // (mid row parity, mid column parity)
+struct SymK {
+    float p[4][5];         // forward: Horner coefficients (degree 5 .. 1) of P(s_ph t) in -t; P(0) = -1
+    float sw[4];           // adjoint: kappa * s_ph
+    float dn[4];           // folded down taps by the phase class they read
+};
+
+__device__ __forceinline__ void gelu_hat_x2(float &a, float &b, const float (&ca)[5], const float (&cb)[5])
 {
-    // two register sets used ping-pong so that "row i+1 becomes row i" costs no moves
-    float x0[6], x1[6], d0[6], d1[6], m0[9], m1[9];
+    const f32x2 sv = pack2(-fabsf(a), -fabsf(b));
+    f32x2 p = pack2(ca[0], cb[0]);
+    p = fma2(p, sv, pack2(ca[1], cb[1]));
+    p = fma2(p, sv, pack2(ca[2], cb[2]));
+    p = fma2(p, sv, pack2(ca[3], cb[3]));
+    p = fma2(p, sv, pack2(ca[4], cb[4]));
+    p = fma2(p, sv, splat2(AFR_P0));
+    float pa, pb;
+    unpack2(p, pa, pb);
+    unpack2(fma2(sv, pack2(ex2_approx(pa), ex2_approx(pb)), pack2(relu_nan(a), relu_nan(b))), a, b);
+}
+
+// xi (and delta) of mid rows 2i (e) and 2i+1 (o), columns M0 .. (M0 == 0 ? 0 : 8)
+template <int M0>
+__device__ __forceinline__ void sym_sums(const float (&xa)[6], const float (&ha)[5], const float (&xb)[6],
+                                         const float (&hb)[5], float (&e)[9], float (&o)[9])
+{
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { d0[c] = 0.f; d1[c] = 0.f; }
-    sx.load(i0, x0);
-    if (kBwd) sd.load(i0, d0);
-    // mid row 2*i0-1.  The branch is warp-uniform (a warp that holds both a first and a later
-    // row segment computes it on all lanes and zeroes it below) so that the warp stays converged
-    // for the shuffles; planes that fit one segment (4x4, 8x8) skip it altogether.
-    if (__any_sync(0xffffffffu, i0 > 0)) {
-    sx.load(i0 - 1, x1);
+    for (int m = M0; m < (M0 == 0 ? 1 : 9); ++m) {
+        if (m & 1) {
+            e[m] = xa[(m + 1) / 2];
+            o[m] = xa[(m + 1) / 2] + xb[(m + 1) / 2];
+        } else if (m == 0) {                         // only the column-0 branch needs h[0]
+            const float h0a = xa[0] + xa[1];
+            e[m] = h0a;
+            o[m] = h0a + (xb[0] + xb[1]);
+        } else {
+            e[m] = ha[m / 2];
+            o[m] = ha[m / 2] + hb[m / 2];
+        }
+    }
+}
+
+template <bool kBwd, class SX, class SD, typename TO>
+__device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__restrict__ out, int W, int i,
+                                           bool store, bool first_col, bool own0, const SymK &K,
+                                           const RowSet &A, RowSet &B)
+{
+    sx.load(i + 1, B.x);
+    if (kBwd) sd.load(i + 1, B.d);
+#pragma unroll
+    for (int c = 1; c < 5; ++c) {
+        B.hx[c] = B.x[c] + B.x[c + 1];
+        if (kBwd) B.hd[c] = B.d[c] + B.d[c + 1];
+    }
+    float me[9], mo[9];
     if (kBwd) {
-        float u[9];
-        sd.load(i0 - 1, d1);
-        up_odd_cols<1>(x1, x0, kU, u);
-        up_odd_cols<1>(d1, d0, kG, m0);
-        act_cols_1_8<true>(u, m0);
+        float ue[9], uo[9];
+        sym_sums<1>(A.x, A.hx, B.x, B.hx, ue, uo);
+        sym_sums<1>(A.d, A.hd, B.d, B.hd, me, mo);
+#pragma unroll
+        for (int m = 1; m < 9; ++m) {
+            ue[m] *= K.sw[(m & 1) ? PH_EE : PH_EO];
+            uo[m] *= K.sw[(m & 1) ? PH_OE : PH_OO];
+        }
+        act_cols_1_8<true>(ue, me);
+        act_cols_1_8<true>(uo, mo);
         if (own0) {
-            up_odd_cols<0>(x1, x0, kU, u);
-            up_odd_cols<0>(d1, d0, kG, m0);
-            act_col0_single<true>(u, m0);
+            sym_sums<0>(A.x, A.hx, B.x, B.hx, ue, uo);
+            sym_sums<0>(A.d, A.hd, B.d, B.hd, me, mo);
+            ue[0] *= K.sw[PH_EO];
+            uo[0] *= K.sw[PH_OO];
+            act_col0_pair<true>(ue, uo, me, mo);
         }
     } else {
-        up_odd_cols<1>(x1, x0, kU, m0);
-        act_cols_1_8<false>(m0, m0);
+        sym_sums<1>(A.x, A.hx, B.x, B.hx, me, mo);
+        gelu_hat_x2(me[1], me[3], K.p[PH_EE], K.p[PH_EE]);
+        gelu_hat_x2(me[5], me[7], K.p[PH_EE], K.p[PH_EE]);
+        gelu_hat_x2(me[2], me[4], K.p[PH_EO], K.p[PH_EO]);
+        gelu_hat_x2(me[6], me[8], K.p[PH_EO], K.p[PH_EO]);
+        gelu_hat_x2(mo[1], mo[3], K.p[PH_OE], K.p[PH_OE]);
+        gelu_hat_x2(mo[5], mo[7], K.p[PH_OE], K.p[PH_OE]);
+        gelu_hat_x2(mo[2], mo[4], K.p[PH_OO], K.p[PH_OO]);
+        gelu_hat_x2(mo[6], mo[8], K.p[PH_OO], K.p[PH_OO]);
         if (own0) {
-            up_odd_cols<0>(x1, x0, kU, m0);
-            act_col0_single<false>(m0, m0);
+            sym_sums<0>(A.x, A.hx, B.x, B.hx, me, mo);
+            gelu_hat_x2(me[0], mo[0], K.p[PH_EO], K.p[PH_OO]);
         }
     }
-    {
-        const float l = __shfl_up_sync(0xffffffffu, m0[8], 1);
-        if (!own0) m0[0] = l;
-    }
-    if (first_col) m0[0] = 0.f;
-    }
-    if (i0 == 0) {                                  // row -1 lies outside the 2x grid: mid == 0
+    const float le = __shfl_up_sync(0xffffffffu, me[8], 1), lo = __shfl_up_sync(0xffffffffu, mo[8], 1);
+    if (!own0) { me[0] = le; mo[0] = lo; }
+    if (first_col) { me[0] = 0.f; mo[0] = 0.f; }
+    float o[4];
 #pragma unroll
-        for (int c = 0; c < 9; ++c) m0[c] = 0.f;
+    for (int q = 0; q < 4; ++q) {
+        float ro = K.dn[PH_OE] * mo[2 * q + 1];
+        ro = fmaf(K.dn[PH_OO], mo[2 * q] + mo[2 * q + 2], ro);
+        B.r[q] = ro;
+        float acc = fmaf(K.dn[PH_EO], me[2 * q] + me[2 * q + 2], A.r[q]);
+        acc = fmaf(K.dn[PH_EE], me[2 * q + 1], acc);
+        o[q] = acc + ro;
     }
+    if (store) st4(out + (long)i * W, make_float4(o[0], o[1], o[2], o[3]));
+}
+
+template <class KT> struct IsSym { static constexpr bool value = false; };
+template <> struct IsSym<SymK> { static constexpr bool value = true; };
+
+// state before the first step of a strip: input row i0 in A, nothing above it yet
+template <bool kBwd, class KT, class SX, class SD>
+__device__ __forceinline__ void strip_begin(const SX &sx, const SD &sd, int i0, RowSet &A)
+{
+    sx.load(i0, A.x);
+    if (kBwd) sd.load(i0, A.d);
+    if (IsSym<KT>::value) {
+#pragma unroll
+        for (int c = 1; c < 5; ++c) {
+            A.hx[c] = A.x[c] + A.x[c + 1];
+            if (kBwd) A.hd[c] = A.d[c] + A.d[c + 1];
+        }
+    }
+}
+
+__device__ __forceinline__ void clear_carry(RowSet &A)     // mid row -1 lies outside the 2x grid
+{
+#pragma unroll
+    for (int c = 0; c < 9; ++c) A.m[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) A.r[c] = 0.f;
+}
+
+// R steps starting at row i0 (R is warp-uniform); rows >= i1 are computed but not stored.
+template <bool kBwd, class KT, class SX, class SD, typename TO>
+__device__ __forceinline__ void strip_core(const SX &sx, const SD &sd, TO *__restrict__ out, int W,
+                                           int i0, int i1, int R, bool valid, bool first_col, bool own0,
+                                           const KT &K)
+{
+    RowSet S0, S1;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { S0.d[c] = 0.f; S1.d[c] = 0.f; }
+    // The carried mid row 2*i0-1 comes from one dry step at row i0-1 (nothing stored).  The branch
+    // is warp-uniform (a warp that holds both a first and a later row segment runs it on all lanes
+    // and zeroes the carry below) so that the warp stays converged for the shuffles; planes that fit
+    // one segment (4x4, 8x8) skip it altogether.
+    clear_carry(S1);
+    if (__any_sync(0xffffffffu, i0 > 0)) {
+        strip_begin<kBwd, KT>(sx, sd, i0 - 1, S1);
+        strip_step<kBwd>(sx, sd, out, W, i0 - 1, false, first_col, own0, K, S1, S0);
+    } else {
+        strip_begin<kBwd, KT>(sx, sd, i0, S0);
+    }
+    if (i0 == 0) clear_carry(S0);
     const int iend = i0 + R;
     int i = i0;
     for (; i + 1 < iend; i += 2) {
-        strip_step<kBwd>(sx, sd, out, W, i, valid && i < i1, first_col, own0, kU, kG, kB, x0, x1, d0, d1, m0, m1);
-        strip_step<kBwd>(sx, sd, out, W, i + 1, valid && i + 1 < i1, first_col, own0, kU, kG, kB, x1, x0, d1, d0, m1, m0);
+        strip_step<kBwd>(sx, sd, out, W, i, valid && i < i1, first_col, own0, K, S0, S1);
+        strip_step<kBwd>(sx, sd, out, W, i + 1, valid && i + 1 < i1, first_col, own0, K, S1, S0);
     }
-    if (i < iend)
-        strip_step<kBwd>(sx, sd, out, W, i, valid && i < i1, first_col, own0, kU, kG, kB, x0, x1, d0, d1, m0, m1);
+    if (i < iend) strip_step<kBwd>(sx, sd, out, W, i, valid && i < i1, first_col, own0, K, S0, S1);
 }
 
 // ---------------------------------------------------------------------------------
 // direct kernel
 // ---------------------------------------------------------------------------------
-template <typename T, bool kBwd, bool kRes, bool kAff>
+template <typename T, bool kBwd, bool kRes, bool kAff, class KT>
 __global__ void __launch_bounds__(256)
 fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T *__restrict__ dy,
                      const float *__restrict__ scale, const float *__restrict__ shift,
                      T *__restrict__ out, long planes, int H, int W, int strips, int nseg, int R,
-                     const __grid_constant__ Taps3 kU, const __grid_constant__ Taps3 kG,
-                     const __grid_constant__ Taps3 kB)
+                     const __grid_constant__ KT K)
 {
     // 32-bit index arithmetic (the launcher guarantees planes * strips * nseg < 2^31)
     unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,7 +465,7 @@ fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T
         if (kRes) asm volatile("prefetch.global.L1 [%0];" ::"l"(res + base + (long)r * W));
         if (kBwd) asm volatile("prefetch.global.L1 [%0];" ::"l"(dy + base + (long)r * W));
     }
-    strip_core<kBwd>(sx, sd, out + base, W, i0, i1, R, valid, j == 0, own0, kU, kG, kB);
+    strip_core<kBwd, KT>(sx, sd, out + base, W, i0, i1, R, valid, j == 0, own0, K);
 }
 
 // ---------------------------------------------------------------------------------
@@ -410,13 +541,12 @@ struct TileCfg {
 #ifndef AFR_TMA_MINB
 #define AFR_TMA_MINB 1
 #endif
-template <typename T, bool kBwd, bool kRes, bool kAff>
+template <typename T, bool kBwd, bool kRes, bool kAff, class KT>
 __global__ void __launch_bounds__(128, AFR_TMA_MINB)
 fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mres,
                   const __grid_constant__ CUtensorMap mdy, const float *__restrict__ scale,
                   const float *__restrict__ shift, T *__restrict__ out, long planes, int H,
-                  int W, const __grid_constant__ TileCfg cfg, const __grid_constant__ Taps3 kU,
-                  const __grid_constant__ Taps3 kG, const __grid_constant__ Taps3 kB)
+                  int W, const __grid_constant__ TileCfg cfg, const __grid_constant__ KT K)
 {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ __align__(8) uint64_t full[2];
@@ -469,11 +599,10 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     T *dst = out + (p0 + pl) * (long)H * W + (valid ? j : 0);
     const Affine aff = make_affine(kAff ? scale : nullptr, shift, p0 + pl, p0 + pl < planes, j, W);
 
-    float x0[6], x1[6], d0[6], d1[6], m0[9], m1[9];
+    RowSet S0, S1;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { d0[c] = 0.f; d1[c] = 0.f; }
-#pragma unroll
-    for (int c = 0; c < 9; ++c) m0[c] = 0.f;        // mid row -1 lies outside the 2x grid
+    for (int c = 0; c < 6; ++c) { S0.d[c] = 0.f; S1.d[c] = 0.f; }
+    clear_carry(S0);                                // mid row -1 lies outside the 2x grid
 
     for (int k = 0; k < nchunks; ++k) {
         const unsigned char *base = tile_smem + (k & 1) * stage_bytes;
@@ -484,15 +613,11 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
         TileRows<T, kRes, kAff> sx{xs + toff, rs + toff, pitch, r0, H, aff};
         TileRows<T, false> sd{ds + toff, nullptr, pitch, r0, H, Affine{0.f, 0.f, 0.f, 0.f}};
         mbar_wait(&full[k & 1], (k >> 1) & 1);
-        if (k == 0) {
-            sx.load(r0, x0);
-            if (kBwd) sd.load(r0, d0);
-        }
-        for (int i = r0; i < r0 + cfg.R; i += 2) {   // R is even: register roles return to x0/m0
-            strip_step<kBwd>(sx, sd, dst, W, i, valid && i >= seg_lo && i < seg_hi, first_col, own0, kU, kG, kB,
-                             x0, x1, d0, d1, m0, m1);
-            strip_step<kBwd>(sx, sd, dst, W, i + 1, valid && i + 1 >= seg_lo && i + 1 < seg_hi, first_col, own0, kU,
-                             kG, kB, x1, x0, d1, d0, m1, m0);
+        if (k == 0) strip_begin<kBwd, KT>(sx, sd, r0, S0);
+        for (int i = r0; i < r0 + cfg.R; i += 2) {   // R is even: register roles return to S0
+            strip_step<kBwd>(sx, sd, dst, W, i, valid && i >= seg_lo && i < seg_hi, first_col, own0, K, S0, S1);
+            strip_step<kBwd>(sx, sd, dst, W, i + 1, valid && i + 1 >= seg_lo && i + 1 < seg_hi, first_col, own0, K,
+                             S1, S0);
         }
         __syncthreads();                            // stage k & 1 fully consumed
         if (threadIdx.x == 0 && k + 2 < nchunks) issue(k + 2);
@@ -695,19 +820,18 @@ static bool make_plane_map(CUtensorMap *m, const void *base, long planes, int H,
 
 static inline int pick_rows(int H) { return H < 8 ? H : 8; }
 
-template <typename T, bool kBwd, bool kRes, bool kAff>
+template <typename T, bool kBwd, bool kRes, bool kAff, class KT>
 static cudaError_t launch_direct(const void *x, const void *res, const void *dy, const float *scale,
                                  const float *shift, void *out, long planes, int H, int W,
-                                 const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, cudaStream_t s)
+                                 const KT &K, cudaStream_t s)
 {
     const int strips = W / 4, R = pick_rows(H), nseg = (H + R - 1) / R;
     const long total = planes * (long)strips * nseg;
     const int block = 128;
     const long grid = (total + block - 1) / block;
     if (total >= 0x7fffffffL) { set_detail("tensor too large for the direct kernel's 32-bit indexing"); return cudaErrorInvalidConfiguration; }
-    fgelu3_direct_kernel<T, kBwd, kRes, kAff><<<(unsigned)grid, block, 0, s>>>(
-        (const T *)x, (const T *)res, (const T *)dy, scale, shift, (T *)out, planes, H, W, strips, nseg, R,
-        kU, kG, kB);
+    fgelu3_direct_kernel<T, kBwd, kRes, kAff, KT><<<(unsigned)grid, block, 0, s>>>(
+        (const T *)x, (const T *)res, (const T *)dy, scale, shift, (T *)out, planes, H, W, strips, nseg, R, K);
     return cudaGetLastError();
 }
 
@@ -772,10 +896,10 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
     return false;
 }
 
-template <typename T, bool kBwd, bool kRes, bool kAff>
+template <typename T, bool kBwd, bool kRes, bool kAff, class KT>
 static cudaError_t launch_tma(const void *x, const void *res, const void *dy, const float *scale,
                               const float *shift, void *out, long planes, int H, int W, int dtype,
-                              const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, cudaStream_t s)
+                              const KT &K, cudaStream_t s)
 {
     const int nin = 1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0);
     int threads; TileCfg cfg;
@@ -791,33 +915,75 @@ static cudaError_t launch_tma(const void *x, const void *res, const void *dy, co
     if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
     const dim3 grid3((unsigned)grid, (unsigned)cfg.nsegs);
     const size_t smem = (size_t)cfg.tile_bytes * nin * 2;
-    auto kern = fgelu3_tma_kernel<T, kBwd, kRes, kAff>;
+    auto kern = fgelu3_tma_kernel<T, kBwd, kRes, kAff, KT>;
     static bool attr_set = false;     // per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) { set_detail("cudaFuncSetAttribute(max dynamic smem) failed"); return e; }
         attr_set = true;
     }
-    kern<<<grid3, threads, smem, s>>>(mx, mres, mdy, scale, shift, (T *)out, planes, H, W, cfg, kU, kG, kB);
+    kern<<<grid3, threads, smem, s>>>(mx, mres, mdy, scale, shift, (T *)out, planes, H, W, cfg, K);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         set_detail("launch grid=%ld block=%d smem=%zu tile Tw=%d R=%d P=%d", grid, threads, smem, cfg.Tw, cfg.R, cfg.P);
     return e;
 }
 
+// ---- symmetric-tap fast path: eligibility and host-side coefficient folding ---------------------
+static bool d4_symmetric(const Taps3 &t)
+{
+    return t.k[0][0] == t.k[0][2] && t.k[0][0] == t.k[2][0] && t.k[0][0] == t.k[2][2] &&
+           t.k[0][1] == t.k[2][1] && t.k[1][0] == t.k[1][2];
+}
+
+static void phase_taps(const Taps3 &t, double (&s)[4])
+{
+    s[PH_EE] = t.k[1][1]; s[PH_EO] = t.k[1][0]; s[PH_OE] = t.k[0][1]; s[PH_OO] = t.k[0][0];
+}
+
+// false: the taps do not qualify (asymmetric, or a negative / non-finite up tap in the forward,
+// where gelu(s xi) = s ghat(xi) needs s >= 0) and the general kernels run instead
+static bool make_sym(const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd, SymK *K)
+{
+    if (!d4_symmetric(kU) || !d4_symmetric(kB) || (bwd && !d4_symmetric(kG))) return false;
+    double su[4], sb[4], sg[4];
+    phase_taps(kU, su); phase_taps(kB, sb); phase_taps(kG, sg);
+    static const double P[5] = {-(double)AFR_P5, (double)AFR_P4, -(double)AFR_P3, (double)AFR_P2, -(double)AFR_P1};
+    for (int ph = 0; ph < 4; ++ph) {
+        if (!bwd && !(su[ph] >= 0.0 && su[ph] < 1e30)) return false;
+        double pw = su[ph] * su[ph] * su[ph] * su[ph] * su[ph];          // s^5 .. s^1
+        for (int k = 0; k < 5; ++k) {
+            K->p[ph][k] = (float)(P[k] * pw);
+            pw = su[ph] != 0.0 ? pw / su[ph] : 0.0;
+        }
+        K->sw[ph] = (float)su[ph];                                       // adjoint: kU arrives kappa-scaled
+        K->dn[ph] = (float)(sb[ph] * (bwd ? sg[ph] : su[ph]));
+    }
+    return true;
+}
+
 cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, const float *scale, const float *shift,
                      void *out, long planes, int H, int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB,
-                     bool bwd, int dtype, bool use_tma, cudaStream_t s, const char **kernel_name)
+                     bool bwd, int dtype, bool use_tma, bool allow_sym, cudaStream_t s, const char **kernel_name)
 {
-#define AFR_GO(T, B, R, A)                                                                                   \
-    return use_tma ? launch_tma<T, B, R, A>(x, res, dy, scale, shift, out, planes, H, W, dtype, kU, kG, kB, s) \
-                   : launch_direct<T, B, R, A>(x, res, dy, scale, shift, out, planes, H, W, kU, kG, kB, s)
+#define AFR_GO(T, B, R, A)                                                                                          \
+    do {                                                                                                            \
+        if (sym) return use_tma ? launch_tma<T, B, R, A, SymK>(x, res, dy, scale, shift, out, planes, H, W, dtype, KS, s) \
+                                : launch_direct<T, B, R, A, SymK>(x, res, dy, scale, shift, out, planes, H, W, KS, s);   \
+        return use_tma ? launch_tma<T, B, R, A, StepK>(x, res, dy, scale, shift, out, planes, H, W, dtype, KG, s)   \
+                       : launch_direct<T, B, R, A, StepK>(x, res, dy, scale, shift, out, planes, H, W, KG, s);      \
+    } while (0)
 #define AFR_GO_T(T)                                                                                          \
     if (bwd) { if (res) { AFR_GO(T, true, true, false); } else { AFR_GO(T, true, false, false); } }          \
     else if (scale) { if (res) { AFR_GO(T, false, true, true); } else { AFR_GO(T, false, false, true); } }   \
     else { if (res) { AFR_GO(T, false, true, false); } else { AFR_GO(T, false, false, false); } }
-    if (kernel_name) *kernel_name = use_tma ? "fgelu3_tma_kernel" : "fgelu3_direct_kernel";
     if (bwd && scale) { set_detail("affine fusion is forward-only"); return cudaErrorNotSupported; }
+    SymK KS;
+    const StepK KG = {kU, kG, kB};
+    const bool sym = allow_sym && make_sym(kU, kG, kB, bwd, &KS);
+    if (kernel_name)
+        *kernel_name = use_tma ? (sym ? "fgelu3_tma_kernel<sym>" : "fgelu3_tma_kernel")
+                               : (sym ? "fgelu3_direct_kernel<sym>" : "fgelu3_direct_kernel");
     if (dtype == AFR_F32) { AFR_GO_T(float) }
     AFR_GO_T(bf16)
 #undef AFR_GO_T

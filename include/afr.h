@@ -50,7 +50,9 @@ typedef enum {
     AFR_PATH_AUTO = 0,      /* TMA-staged tiles when the shape allows, else direct */
     AFR_PATH_DIRECT = 1,    /* register-strip kernel reading global memory directly */
     AFR_PATH_TMA = 2,       /* force the TMA tile kernel (error if shape unsupported) */
-    AFR_PATH_GENERIC = 3    /* force the runtime-N shared-memory kernels */
+    AFR_PATH_GENERIC = 3,   /* force the runtime-N shared-memory kernels */
+    AFR_PATH_DIRECT_GENERAL = 4, /* DIRECT without the symmetric-tap fast path (general 3x3 taps) */
+    AFR_PATH_TMA_GENERAL = 5     /* TMA without the symmetric-tap fast path */
 } afr_path;
 
 int afr_version(void);

@@ -94,7 +94,7 @@ def test_groupnorm_fusion_inference_matches_reference(afr):
         args = ins + ([dev(g["t"])] if tag.startswith(("Down", "Up")) else [])
         with torch.no_grad():
             fused = mod(*args)
-            assert afr.last_kernel() in ("fgelu3_tma_kernel", "fgelu3_direct_kernel")
+            assert afr.last_kernel() in ("fgelu3_tma_kernel<sym>", "fgelu3_direct_kernel<sym>")
             blocks.FUSE_GROUPNORM_INFERENCE = False
             try:
                 unfused = mod(*args)
@@ -130,7 +130,7 @@ def test_affine_kernel_vs_oracle(afr, oracle):
         sc = (1.0 + 0.5 * rng.standard_normal(shape[:2])).astype(np.float32)
         sh = rng.standard_normal(shape[:2]).astype(np.float32)
         xhat = x * sc[:, :, None, None] + sh[:, :, None, None]
-        for path in ("auto", "direct"):
+        for path in ("auto", "direct", "direct_general"):
             afr.set_path(path)
             try:
                 got = afr.ops.filtered_gelu_affine(dev(x), dev(sc), dev(sh), k, k)

@@ -41,9 +41,9 @@ def _paths_for(afr, name, g):
     H, W = g[f"{name}.x"].shape[-2:]
     paths = ["auto", "generic"]
     if n == 3 and g[f"{name}.kd"].shape[0] == 3 and W % 4 == 0:
-        paths.append("direct")
+        paths += ["direct", "direct_general"]
         if H >= 16 and W >= 16:
-            paths.append("tma")
+            paths += ["tma", "tma_general"]
     return paths
 
 
@@ -126,6 +126,48 @@ def test_oracle_fp32(afr, oracle, shape):
             afr.set_path("auto")
 
 
+SYM_TAPS = [  # (omega_up, beta_up, omega_down, beta_down): every filter the reference can design is D4-symmetric
+    (np.pi / 2, 2.0, np.pi / 2, 2.0), (np.pi / 2, None, 0.7 * np.pi, 1.0), (0.3 * np.pi, 0.0, np.pi, 8.0),
+    (np.pi, 8.0, np.pi / 2, 2.0),   # negative corner tap in the up filter: forward falls back, adjoint folds
+]
+
+
+@pytest.mark.parametrize("taps", SYM_TAPS)
+@pytest.mark.parametrize("shape", [s_[:4] for s_ in ORACLE_SHAPES if s_[4] == 3 and s_[5] == 3 and s_[3] % 4 == 0])
+def test_oracle_fp32_symmetric_taps(afr, oracle, shape, taps):
+    """The folded-tap (symmetric) variants of the N == 3 kernels against the oracle and against the
+    general-tap variants, forward / adjoint / fused residual, every path the shape allows."""
+    B, C, H, W = shape
+    rng = np.random.default_rng(hash((shape, taps[0])) % (2 ** 31))
+    ku = oracle.lowpass_taps(taps[0], 3, taps[1]).astype(np.float32)
+    kd = oracle.lowpass_taps(taps[2], 3, taps[3]).astype(np.float32)
+    x, r, dy = (rng.standard_normal((B, C, H, W)).astype(np.float32) for _ in range(3))
+    want = dict(f=oracle.filtered_gelu(x, ku, kd), f_b=oracle.filtered_gelu_bwd(x, dy, ku, kd),
+                fr=oracle.filtered_gelu(x + r, ku, kd), fr_b=oracle.filtered_gelu_bwd(x + r, dy, ku, kd))
+    paths = ["auto", "direct", "direct_general"] + (["tma", "tma_general"] if H >= 2 and W >= 8 else [])
+    fwd_sym = float(ku.min()) >= 0
+    for path in paths:
+        afr.set_path(path)
+        try:
+            xt, rt = dev(x, grad=True), dev(r, grad=True)
+            y = afr.filtered_gelu(xt, ku, kd)
+            if path != "auto":
+                assert afr.last_kernel().endswith("<sym>") == (fwd_sym and not path.endswith("general")), path
+            assert relmax(host(y), want["f"]) <= FP32_TOL, path
+            (gx,) = torch.autograd.grad(y, xt, dev(dy))
+            if path != "auto":      # (autograd runs the adjoint on its own thread; last_kernel is per thread)
+                afr.ops._fgelu_bwd(xt.detach(), None, dev(dy), afr.Taps(ku), afr.Taps(kd))
+                assert afr.last_kernel().endswith("<sym>") == (not path.endswith("general")), path
+            assert relmax(host(gx), want["f_b"]) <= FP32_TOL, path
+            y = afr.filtered_gelu(xt, ku, kd, residual=rt)
+            assert relmax(host(y), want["fr"]) <= FP32_TOL, path
+            gx, gr = torch.autograd.grad(y, (xt, rt), dev(dy))
+            assert relmax(host(gx), want["fr_b"]) <= FP32_TOL, path
+            assert torch.equal(gx, gr)
+        finally:
+            afr.set_path("auto")
+
+
 @pytest.mark.parametrize("shape", [(2, 4, 32, 32), (1, 2, 64, 64), (9, 3, 4, 4), (2, 2, 16, 24), (1, 2, 9, 7),
                                    (3, 2, 10, 12), (2, 1, 6, 20), (1, 3, 24, 136)])
 @pytest.mark.parametrize("n", [3, 6])
@@ -135,7 +177,7 @@ def test_oracle_bf16(afr, oracle, shape, n):
     xb = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
     dyb = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
     x32, dy32 = host(xb), host(dyb)
-    for path in (["auto", "generic", "direct"] if (n == 3 and shape[-1] % 4 == 0) else ["auto"]):
+    for path in (["auto", "generic", "direct", "direct_general"] if (n == 3 and shape[-1] % 4 == 0) else ["auto"]):
         afr.set_path(path)
         try:
             xt = xb.clone().requires_grad_(True)
@@ -178,7 +220,7 @@ def test_full_size_properties(afr, oracle):
     # fused: all kernel families agree, and match the oracle on sampled planes
     outs = {}
     dy = torch.randn_like(x)
-    for path in ("tma", "direct", "generic"):
+    for path in ("tma", "direct", "generic", "tma_general"):
         afr.set_path(path)
         try:
             xg = x.clone().requires_grad_(True)
@@ -186,7 +228,7 @@ def test_full_size_properties(afr, oracle):
             outs[path] = (y.detach(), torch.autograd.grad(y, xg, dy)[0])
         finally:
             afr.set_path("auto")
-    for path in ("direct", "generic"):
+    for path in ("direct", "generic", "tma_general"):
         assert (outs[path][0] - outs["tma"][0]).abs().max().item() <= 2e-6
         assert (outs[path][1] - outs["tma"][1]).abs().max().item() <= 2e-6
     kn = k.numpy()
@@ -199,9 +241,21 @@ def test_full_size_properties(afr, oracle):
 def test_kernel_selection(afr):
     k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
     afr.filtered_gelu(torch.randn(2, 2, 32, 32, device="cuda"), k, k)
-    assert afr.last_kernel() == "fgelu3_tma_kernel"
+    assert afr.last_kernel() == "fgelu3_tma_kernel<sym>"          # D4-symmetric taps: folded-tap variant
     afr.filtered_gelu(torch.randn(2, 2, 4, 4, device="cuda"), k, k)
+    assert afr.last_kernel() == "fgelu3_direct_kernel<sym>"
+    ka = k.clone(); ka[0, 1] += 0.01                                # asymmetric taps: general 3x3 variant
+    afr.filtered_gelu(torch.randn(2, 2, 32, 32, device="cuda"), ka, k)
+    assert afr.last_kernel() == "fgelu3_tma_kernel"
+    afr.filtered_gelu(torch.randn(2, 2, 4, 4, device="cuda"), k, ka)
     assert afr.last_kernel() == "fgelu3_direct_kernel"
+    kneg = afr.circularLowpassKernel(np.pi, 3, 8)                   # negative corner tap in the up filter:
+    assert float(kneg.min()) < 0                                    # forward needs s >= 0 -> general variant,
+    xg = torch.randn(2, 2, 32, 32, device="cuda", requires_grad=True)
+    y = afr.filtered_gelu(xg, kneg, k)
+    assert afr.last_kernel() == "fgelu3_tma_kernel"
+    afr.ops._fgelu_bwd(xg.detach(), None, torch.ones_like(y), afr.Taps(kneg), afr.Taps(k))
+    assert afr.last_kernel() == "fgelu3_tma_kernel<sym>"          # the adjoint has no sign restriction
     k6 = afr.circularLowpassKernel(np.pi / 2, 6, 2)
     afr.filtered_gelu(torch.randn(2, 2, 8, 8, device="cuda"), k6, k6)
     assert afr.last_kernel() == "fgelu_generic_kernel"
@@ -357,7 +411,7 @@ def test_extreme_inputs(afr, oracle):
     x[0, 0, 3, 5] = 0.0
     dy = rng.standard_normal(x.shape).astype(np.float32)
     want_y, want_dx = oracle.filtered_gelu(x, k, k), oracle.filtered_gelu_bwd(x, dy, k, k)
-    for path in ("tma", "direct", "generic"):
+    for path in ("tma", "direct", "generic", "tma_general", "direct_general"):
         afr.set_path(path)
         try:
             xt = dev(x, grad=True)
