@@ -868,6 +868,7 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
     // 128-thread CTAs unless that leaves fewer than ~6 CTAs per SM: long-lived streaming CTAs
     // need a few waves to balance, so small batches of large planes use smaller CTAs
     int th = 128;
+    if (const char *e = getenv("AFR_CTA_THREADS")) th = atoi(e);   // tuning runs
     while (th > 32 && th > c.strips && (planes * c.tiles_x * c.strips) / th < 6 * 148) th /= 2;
     if (th < c.strips) th = c.strips;
     if (th > 128) return false;
