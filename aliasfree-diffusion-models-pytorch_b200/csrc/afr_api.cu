@@ -282,6 +282,11 @@ static int fused_common(const void *x, const void *residual, const void *dy, voi
     set_taps(tU, taps_up, N_up, false);
     set_taps(tG, taps_down, N_down, true);
     if (bwd) set_taps(tB, taps_up, N_up, true); else set_taps(tB, taps_down, N_down, false);
+    if (path == AFR_PATH_AUTO && N_up == N_down && stripn_supported(N_up, H, W, x, residual, bwd ? dy : nullptr, out, dtype)) {
+        g_last_kernel = "fgelu_strip_kernel";
+        return cuda_status(stripn_fgelu(x, residual, dy, out, planes, H, W, tU, tG, tB, bwd, dtype, s),
+                           "fgelu_strip_kernel");
+    }
     g_last_kernel = "fgelu_generic_kernel";
     return cuda_status(generic_fgelu(x, residual, dy, out, planes, H, W, tU, tG, tB, bwd, dtype, s),
                        "fgelu_generic_kernel");

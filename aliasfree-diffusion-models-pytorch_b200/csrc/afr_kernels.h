@@ -18,6 +18,12 @@ cudaError_t generic_fgelu(const void *x, const void *res, const void *dy, void *
                           int H, int W, const TapsG &tU, const TapsG &tG, const TapsG &tB,
                           bool bwd, int dtype, cudaStream_t s);
 
+// afr_stripn.cu -- register-strip fused kernels for N in {2,4,5,6,7,8} (both filters the same size)
+bool stripn_supported(int N, int H, int W, const void *x, const void *res, const void *dy, const void *out,
+                      int dtype);
+cudaError_t stripn_fgelu(const void *x, const void *res, const void *dy, void *out, long planes, int H, int W,
+                         const TapsG &tU, const TapsG &tG, const TapsG &tB, bool bwd, int dtype, cudaStream_t s);
+
 // afr_n3.cu -- N == 3 register-strip kernels (direct and TMA-staged)
 // All take stage taps already arranged for the stencil they run (see afr_api.cu).
 bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype);

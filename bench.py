@@ -280,15 +280,16 @@ def sweep(afr, quick, grid=False):
                 "down2x_fwd": (lambda: afr.ops._down_fwd(x, afr.Taps(k)), 1.25 * n * es),
             }
             if shape == shapes[0]:
-                ops["filtered_gelu_fwd_N6_generic"] = (lambda: afr.ops._fgelu_fwd(x, None, afr.Taps(k6), afr.Taps(k6)), 2 * n * es)
-                for path in ("direct",):
-                    def f(path=path):
+                ops["filtered_gelu_fwd_N6"] = (lambda: afr.ops._fgelu_fwd(x, None, afr.Taps(k6), afr.Taps(k6)), 2 * n * es)
+                ops["filtered_gelu_bwd_N6"] = (lambda: afr.ops._fgelu_bwd(x, None, dy, afr.Taps(k6), afr.Taps(k6)), 3 * n * es)
+                for path, kk, tag in (("direct", k, "direct"), ("tma_general", k, "general_taps"), ("generic", k6, "N6_generic")):
+                    def f(path=path, kk=kk):
                         afr.set_path(path)
                         try:
-                            afr.ops._fgelu_fwd(x, None, afr.Taps(k), afr.Taps(k))
+                            afr.ops._fgelu_fwd(x, None, afr.Taps(kk), afr.Taps(kk))
                         finally:
                             afr.set_path("auto")
-                    ops["filtered_gelu_fwd_" + path] = (f, 2 * n * es)
+                    ops["filtered_gelu_fwd_" + tag] = (f, 2 * n * es)
             for name, (fn, nbytes) in ops.items():
                 ms = tm(fn)
                 rows.append({"op": name, "shape": list(shape), "dtype": "f32" if es == 4 else "bf16",
@@ -452,7 +453,7 @@ def main():
     ap.add_argument("--ddpm-batch", type=int, default=4096)
     ap.add_argument("--train-batch", type=int, default=256)
     ap.add_argument("--no-train", action="store_true")
-    ap.add_argument("--path", default="auto", choices=["auto", "direct", "tma", "generic"])
+    ap.add_argument("--path", default="auto", choices=["auto", "direct", "tma", "generic", "direct_general", "tma_general"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

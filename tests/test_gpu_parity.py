@@ -126,6 +126,40 @@ def test_oracle_fp32(afr, oracle, shape):
             afr.set_path("auto")
 
 
+STRIP_N_SHAPES = [  # (B, C, H, W): warp-aligned rows, strips that do not divide 32, > 128 wide, tiny, tall (row segments)
+    (2, 3, 16, 16), (1, 2, 20, 12), (1, 1, 9, 136), (3, 2, 4, 4), (1, 1, 1, 8), (1, 1, 2, 4), (1, 1, 3, 20),
+    (1, 2, 96, 8), (2, 40, 8, 8), (1, 1, 40, 264),
+]
+
+
+@pytest.mark.parametrize("n", [2, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("shape", STRIP_N_SHAPES)
+def test_oracle_strip_n(afr, oracle, shape, n):
+    """Register-strip kernels for N != 3 (compile-time N, both filters the same size): forward, adjoint and
+    fused residual against the oracle, with asymmetric taps (catches flipped / mis-padded taps)."""
+    rng = np.random.default_rng(hash((shape, n)) % (2 ** 31))
+    ku = (oracle.lowpass_taps(np.pi / 2, n, 2.0) + 0.02 * rng.standard_normal((n, n))).astype(np.float32)
+    kd = (oracle.lowpass_taps(0.7 * np.pi, n, 1.0) + 0.02 * rng.standard_normal((n, n))).astype(np.float32)
+    x, r, dy = (rng.standard_normal(shape).astype(np.float32) for _ in range(3))
+    xt, rt = dev(x, grad=True), dev(r, grad=True)
+    y = afr.filtered_gelu(xt, ku, kd)
+    assert afr.last_kernel() == "fgelu_strip_kernel"
+    assert relmax(host(y), oracle.filtered_gelu(x, ku, kd)) <= FP32_TOL
+    (gx,) = torch.autograd.grad(y, xt, dev(dy))
+    assert relmax(host(gx), oracle.filtered_gelu_bwd(x, dy, ku, kd)) <= FP32_TOL
+    y = afr.filtered_gelu(xt, ku, kd, residual=rt)
+    assert relmax(host(y), oracle.filtered_gelu(x + r, ku, kd)) <= FP32_TOL
+    gx, gr = torch.autograd.grad(y, (xt, rt), dev(dy))
+    assert relmax(host(gx), oracle.filtered_gelu_bwd(x + r, dy, ku, kd)) <= FP32_TOL
+    assert torch.equal(gx, gr)
+    afr.ops._fgelu_bwd(xt.detach(), None, dev(dy), afr.Taps(ku), afr.Taps(kd))
+    assert afr.last_kernel() == "fgelu_strip_kernel"
+    if shape[-1] % 8 == 0:
+        xb = dev(x, torch.bfloat16)
+        yb = afr.filtered_gelu(xb, ku, kd)
+        assert relmax(host(yb), oracle.filtered_gelu(host(xb), ku, kd)) <= BF16_TOL
+
+
 SYM_TAPS = [  # (omega_up, beta_up, omega_down, beta_down): every filter the reference can design is D4-symmetric
     (np.pi / 2, 2.0, np.pi / 2, 2.0), (np.pi / 2, None, 0.7 * np.pi, 1.0), (0.3 * np.pi, 0.0, np.pi, 8.0),
     (np.pi, 8.0, np.pi / 2, 2.0),   # negative corner tap in the up filter: forward falls back, adjoint folds
@@ -258,7 +292,9 @@ def test_kernel_selection(afr):
     assert afr.last_kernel() == "fgelu3_tma_kernel<sym>"          # the adjoint has no sign restriction
     k6 = afr.circularLowpassKernel(np.pi / 2, 6, 2)
     afr.filtered_gelu(torch.randn(2, 2, 8, 8, device="cuda"), k6, k6)
-    assert afr.last_kernel() == "fgelu_generic_kernel"
+    assert afr.last_kernel() == "fgelu_strip_kernel"              # compile-time-N register strips
+    afr.filtered_gelu(torch.randn(2, 2, 8, 7, device="cuda"), k6, k6)
+    assert afr.last_kernel() == "fgelu_generic_kernel"            # odd width: shared-memory backstop
     n0 = afr.launch_count()
     afr.up2x(torch.randn(1, 1, 8, 8, device="cuda"), k)
     assert afr.launch_count() == n0 + 1
