@@ -158,6 +158,10 @@ int afr_up2x_fwd(const void *x, void *u, int B, int C, int H, int W, const float
         return cuda_status(n3_up_like(x, u, planes, H, W, k, in_dtype, out_dtype, s), "up3_kernel");
     }
     TapsG t; set_taps(t, taps, N, false);
+    if (path == AFR_PATH_AUTO && stripn_resample_supported(N) && n3_up_supported(H, W, x, u, in_dtype, out_dtype)) {
+        g_last_kernel = "upn_kernel";
+        return cuda_status(stripn_up_like(x, u, planes, H, W, t, in_dtype, out_dtype, s), "upn_kernel");
+    }
     g_last_kernel = "up_like_generic_kernel";
     return cuda_status(generic_up_like(x, u, planes, H, W, 2 * H, 2 * W, t, in_dtype, out_dtype, s),
                        "up_like_generic_kernel");
@@ -183,6 +187,10 @@ int afr_up2x_bwd(const void *du, void *dx, int B, int C, int H, int W, const flo
         return cuda_status(n3_down_like(du, dx, planes, 2 * H, 2 * W, k, du_dtype, s), "down3_kernel");
     }
     TapsG t; set_taps(t, taps, N, true);
+    if (path == AFR_PATH_AUTO && stripn_resample_supported(N) && n3_down_supported(2 * H, 2 * W, du, dx, du_dtype)) {
+        g_last_kernel = "downn_kernel";
+        return cuda_status(stripn_down_like(du, dx, planes, 2 * H, 2 * W, t, du_dtype, s), "downn_kernel");
+    }
     g_last_kernel = "down_like_generic_kernel";
     return cuda_status(generic_down_like(du, dx, planes, 2 * H, 2 * W, H, W, t, du_dtype, s),
                        "down_like_generic_kernel");
@@ -206,6 +214,10 @@ int afr_down2x_fwd(const void *v, void *y, int B, int C, int H, int W, const flo
         return cuda_status(n3_down_like(v, y, planes, H, W, k, dtype, s), "down3_kernel");
     }
     TapsG t; set_taps(t, taps, N, false);
+    if (path == AFR_PATH_AUTO && stripn_resample_supported(N) && n3_down_supported(H, W, v, y, dtype)) {
+        g_last_kernel = "downn_kernel";
+        return cuda_status(stripn_down_like(v, y, planes, H, W, t, dtype, s), "downn_kernel");
+    }
     g_last_kernel = "down_like_generic_kernel";
     return cuda_status(generic_down_like(v, y, planes, H, W, (H + 1) / 2, (W + 1) / 2, t, dtype, s),
                        "down_like_generic_kernel");
@@ -231,6 +243,11 @@ int afr_down2x_bwd(const void *dy, void *dv, int B, int C, int H, int W, const f
         return cuda_status(n3_up_like(dy, dv, planes, Ho, Wo, k, dtype, dtype, s), "up3_kernel");
     }
     TapsG t; set_taps(t, taps, N, true);
+    if (path == AFR_PATH_AUTO && stripn_resample_supported(N) && (H % 2) == 0 && (W % 2) == 0 &&
+        n3_up_supported(Ho, Wo, dy, dv, dtype, dtype)) {
+        g_last_kernel = "upn_kernel";
+        return cuda_status(stripn_up_like(dy, dv, planes, Ho, Wo, t, dtype, dtype, s), "upn_kernel");
+    }
     g_last_kernel = "up_like_generic_kernel";
     return cuda_status(generic_up_like(dy, dv, planes, Ho, Wo, H, W, t, dtype, dtype, s),
                        "up_like_generic_kernel");

@@ -24,6 +24,13 @@ bool stripn_supported(int N, int H, int W, const void *x, const void *res, const
 cudaError_t stripn_fgelu(const void *x, const void *res, const void *dy, void *out, long planes, int H, int W,
                          const TapsG &tU, const TapsG &tG, const TapsG &tB, bool bwd, int dtype, cudaStream_t s);
 
+// standalone resamplers for the same N (shape / alignment conditions: n3_up_supported / n3_down_supported)
+bool stripn_resample_supported(int N);
+cudaError_t stripn_up_like(const void *in, void *out, long planes, int H, int W, const TapsG &t, int in_dtype,
+                           int out_dtype, cudaStream_t s);
+cudaError_t stripn_down_like(const void *in, void *out, long planes, int H, int W, const TapsG &t, int dtype,
+                             cudaStream_t s);
+
 // afr_n3.cu -- N == 3 register-strip kernels (direct and TMA-staged)
 // All take stage taps already arranged for the stencil they run (see afr_api.cu).
 bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype);

@@ -256,6 +256,110 @@ fgelu_strip_kernel(const T *__restrict__ x, const T *__restrict__ res, const T *
     }
 }
 
+// ---------------------------------------------------------------------------------
+// standalone resamplers for compile-time N (custom_upsample / custom_downsample with N != 3)
+// ---------------------------------------------------------------------------------
+// up-like: thread = 4 input columns -> 8 output columns of the two output rows 2i, 2i+1, from the
+// same register window of input rows (UpGeom with C0 = 0); 128-bit stores
+template <typename TI, typename TO, int N, int PAD>
+__global__ void __launch_bounds__(256)
+upn_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int H, int W, int strips, int nseg,
+           int R, const __grid_constant__ TapsG t)
+{
+    using G = UpGeom<N, PAD, 0>;
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long per_plane = (long)strips * nseg;
+    if (idx >= planes * per_plane) return;
+    const int s = (int)(idx % strips);
+    const int seg = (int)((idx / strips) % nseg);
+    const long p = idx / per_plane;
+    const int j = 4 * s, i0 = seg * R, i1 = min(H, i0 + R);
+    const TI *src = in + p * (long)H * W;
+    TO *dst = out + p * 4L * H * W + 2 * j;
+    const int W2 = 2 * W;
+    float w[G::NR][G::NC];
+#pragma unroll
+    for (int r = 1; r < G::NR; ++r)
+        load_window_row<TI, false, G::clo(), G::chi()>(src, nullptr, i0 + G::rlo() + r - 1, H, W, j, w[r]);
+    for (int i = i0; i < i1; ++i) {
+#pragma unroll
+        for (int r = 0; r + 1 < G::NR; ++r)
+#pragma unroll
+            for (int c = 0; c < G::NC; ++c) w[r][c] = w[r + 1][c];
+        load_window_row<TI, false, G::clo(), G::chi()>(src, nullptr, i + G::rhi(), H, W, j, w[G::NR - 1]);
+        float e[8], o[8];
+        UpRow<G, N, 0>::run(w, t, e);
+        UpRow<G, N, 1>::run(w, t, o);
+        TO *r0 = dst + (long)(2 * i) * W2;
+        st8(r0, e);
+        st8(r0 + W2, o);
+    }
+}
+
+// down-like: thread = 4 output columns; every input row 2i+C0+e is read once (8 own columns as
+// 128-bit loads plus the halo scalars) and added into the K output rows it belongs to
+template <typename T, int N, int PAD>
+__global__ void __launch_bounds__(256)
+downn_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, int W, int Ho, int Wo,
+             int strips, int nseg, int R, const __grid_constant__ TapsG t)
+{
+    constexpr int C0 = N - 2 - PAD, K = (N - 1) / 2 + 1, HL = PAD, HR = imax(0, N - 2 - PAD);
+    constexpr int NM = imax(N + 6, HL + 8);
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long per_plane = (long)strips * nseg;
+    if (idx >= planes * per_plane) return;
+    const int s = (int)(idx % strips);
+    const int seg = (int)((idx / strips) % nseg);
+    const long p = idx / per_plane;
+    const int j = 4 * s, i0 = seg * R, i1 = min(Ho, i0 + R);
+    const T *plane = in + p * (long)H * W;
+    T *dst = out + p * (long)Ho * Wo + j;
+    float acc[K][4];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[k][q] = 0.f;
+    for (int i = i0 - (K - 1); i < i1; ++i) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int Y = 2 * i + C0 + e;
+            float m[NM];
+            if (Y >= 0 && Y < H) {
+                const T *row = plane + (long)Y * W + 2 * j;
+                float own[8];
+                ld8(row, own);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (HL + c < NM) m[HL + c] = own[c];
+#pragma unroll
+                for (int c = 0; c < HL; ++c) m[c] = (2 * j - HL + c >= 0) ? ld1(row - HL + c) : 0.f;
+#pragma unroll
+                for (int c = 0; c < HR; ++c)
+                    if (HL + 8 + c < NM) m[HL + 8 + c] = (2 * j + 8 + c < W) ? ld1(row + 8 + c) : 0.f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < NM; ++c) m[c] = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int a = N - 2 + e - 2 * k;
+                if (a < 0 || a >= N) continue;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int b = 0; b < N; ++b) acc[k][q] = fmaf(t.k[a * N + b], m[2 * q + b], acc[k][q]);
+            }
+        }
+        if (i >= i0) st4(dst + (long)i * Wo, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]));
+#pragma unroll
+        for (int k = 0; k + 1 < K; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[k][q] = acc[k + 1][q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[K - 1][q] = 0.f;
+    }
+}
+
 // ---- host side --------------------------------------------------------------------
 static inline bool aligned_to(const void *p, size_t a) { return !p || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -309,6 +413,83 @@ cudaError_t stripn_fgelu(const void *x, const void *res, const void *dy, void *o
 #undef AFR_SN
     set_detail("strip kernel: unsupported N=%d", tU.n);
     return cudaErrorInvalidConfiguration;
+}
+
+static inline int rows_per_segment(long planes, int strips, int H, int K, int *nseg_out)
+{
+    int nseg = 1;
+    while (planes * strips * nseg < 148L * 2048 && (H + nseg - 1) / nseg > 4 * K + 4) nseg *= 2;
+    const int R = (H + nseg - 1) / nseg;
+    *nseg_out = (H + R - 1) / R;
+    return R;
+}
+
+bool stripn_resample_supported(int N) { return N == 2 || N == 4 || N == 5 || N == 6 || N == 7 || N == 8; }
+
+// in [planes,H,W] -> out [planes,2H,2W]; `t.pad` must be pl or ph of N
+template <typename TI, typename TO>
+static cudaError_t launch_upn(const void *in, void *out, long planes, int H, int W, const TapsG &t, cudaStream_t s)
+{
+    const int strips = W / 4;
+    int nseg;
+    const int R = rows_per_segment(planes, strips, H, 1, &nseg);
+    const long total = planes * (long)strips * nseg;
+    const long grid = (total + 255) / 256;
+    if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    const int pl = (t.n - 1) / 2;
+#define AFR_UPN(N)                                                                                              \
+    case N:                                                                                                     \
+        if (t.pad == pl)                                                                                        \
+            upn_kernel<TI, TO, N, (N - 1) / 2><<<(unsigned)grid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, H, W, \
+                                                                              strips, nseg, R, t);             \
+        else                                                                                                    \
+            upn_kernel<TI, TO, N, N - 1 - (N - 1) / 2><<<(unsigned)grid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, \
+                                                                                      H, W, strips, nseg, R, t); \
+        break;
+    switch (t.n) { AFR_UPN(2) AFR_UPN(4) AFR_UPN(5) AFR_UPN(6) AFR_UPN(7) AFR_UPN(8) default: return cudaErrorInvalidConfiguration; }
+#undef AFR_UPN
+    return cudaGetLastError();
+}
+
+cudaError_t stripn_up_like(const void *in, void *out, long planes, int H, int W, const TapsG &t, int in_dtype,
+                           int out_dtype, cudaStream_t s)
+{
+    if (in_dtype == AFR_F32 && out_dtype == AFR_F32) return launch_upn<float, float>(in, out, planes, H, W, t, s);
+    if (in_dtype == AFR_BF16 && out_dtype == AFR_BF16) return launch_upn<bf16, bf16>(in, out, planes, H, W, t, s);
+    if (in_dtype == AFR_BF16 && out_dtype == AFR_F32) return launch_upn<bf16, float>(in, out, planes, H, W, t, s);
+    return launch_upn<float, bf16>(in, out, planes, H, W, t, s);
+}
+
+// in [planes,H,W] (W % 8 == 0) -> out [planes,ceil(H/2),W/2]
+template <typename T>
+static cudaError_t launch_downn(const void *in, void *out, long planes, int H, int W, const TapsG &t, cudaStream_t s)
+{
+    const int Ho = (H + 1) / 2, Wo = W / 2, strips = Wo / 4;
+    int nseg;
+    const int R = rows_per_segment(planes, strips, Ho, (t.n - 1) / 2 + 1, &nseg);
+    const long total = planes * (long)strips * nseg;
+    const long grid = (total + 255) / 256;
+    if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    const int pl = (t.n - 1) / 2;
+#define AFR_DNN(N)                                                                                              \
+    case N:                                                                                                     \
+        if (t.pad == pl)                                                                                        \
+            downn_kernel<T, N, (N - 1) / 2><<<(unsigned)grid, 256, 0, s>>>((const T *)in, (T *)out, planes, H, W, Ho, \
+                                                                           Wo, strips, nseg, R, t);            \
+        else                                                                                                    \
+            downn_kernel<T, N, N - 1 - (N - 1) / 2><<<(unsigned)grid, 256, 0, s>>>((const T *)in, (T *)out, planes, H, \
+                                                                                   W, Ho, Wo, strips, nseg, R, t); \
+        break;
+    switch (t.n) { AFR_DNN(2) AFR_DNN(4) AFR_DNN(5) AFR_DNN(6) AFR_DNN(7) AFR_DNN(8) default: return cudaErrorInvalidConfiguration; }
+#undef AFR_DNN
+    return cudaGetLastError();
+}
+
+cudaError_t stripn_down_like(const void *in, void *out, long planes, int H, int W, const TapsG &t, int dtype,
+                             cudaStream_t s)
+{
+    return dtype == AFR_F32 ? launch_downn<float>(in, out, planes, H, W, t, s)
+                            : launch_downn<bf16>(in, out, planes, H, W, t, s);
 }
 
 }  // namespace afr

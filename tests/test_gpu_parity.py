@@ -160,6 +160,38 @@ def test_oracle_strip_n(afr, oracle, shape, n):
         assert relmax(host(yb), oracle.filtered_gelu(host(xb), ku, kd)) <= BF16_TOL
 
 
+@pytest.mark.parametrize("n", [2, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (1, 2, 20, 24), (1, 1, 9, 136), (3, 2, 8, 8), (1, 1, 1, 8),
+                                   (1, 2, 64, 8), (1, 1, 7, 40)])
+def test_oracle_strip_n_resamplers(afr, oracle, shape, n):
+    """custom_upsample / custom_downsample with N != 3 (the reference's default filter size is 6):
+    compile-time-N strip kernels, forward and adjoint, against the oracle; asymmetric taps."""
+    B, C, H, W = shape
+    rng = np.random.default_rng(hash((shape, n, 1)) % (2 ** 31))
+    ku = (oracle.lowpass_taps(np.pi / 2, n, 2.0) + 0.02 * rng.standard_normal((n, n))).astype(np.float32)
+    kd = (oracle.lowpass_taps(0.7 * np.pi, n, 1.0) + 0.02 * rng.standard_normal((n, n))).astype(np.float32)
+    x = rng.standard_normal(shape).astype(np.float32)
+    du = rng.standard_normal((B, C, 2 * H, 2 * W)).astype(np.float32)
+    dd = rng.standard_normal((B, C, (H + 1) // 2, (W + 1) // 2)).astype(np.float32)
+    xt = dev(x, grad=True)
+    u = afr.up2x(xt, ku)
+    assert afr.last_kernel() == "upn_kernel"
+    assert relmax(host(u), oracle.up2x(x, ku)) <= FP32_TOL
+    assert relmax(host(torch.autograd.grad(u, xt, dev(du))[0]), oracle.up2x_bwd(du, ku)) <= FP32_TOL
+    d = afr.down2x(xt, kd)
+    assert afr.last_kernel() == "downn_kernel"
+    assert relmax(host(d), oracle.down2x(x, kd)) <= FP32_TOL
+    assert relmax(host(torch.autograd.grad(d, xt, dev(dd))[0]), oracle.down2x_bwd(dd, kd, H, W)) <= FP32_TOL
+    afr.ops._up_bwd(dev(du), afr.Taps(ku), H, W)
+    assert afr.last_kernel() == "downn_kernel"
+    if H % 2 == 0:
+        afr.ops._down_bwd(dev(dd), afr.Taps(kd), H, W)
+        assert afr.last_kernel() == "upn_kernel"
+    xb = dev(x, torch.bfloat16)
+    assert relmax(host(afr.up2x(xb, ku)), oracle.up2x(host(xb), ku)) <= BF16_TOL
+    assert relmax(host(afr.down2x(xb, kd)), oracle.down2x(host(xb), kd)) <= BF16_TOL
+
+
 SYM_TAPS = [  # (omega_up, beta_up, omega_down, beta_down): every filter the reference can design is D4-symmetric
     (np.pi / 2, 2.0, np.pi / 2, 2.0), (np.pi / 2, None, 0.7 * np.pi, 1.0), (0.3 * np.pi, 0.0, np.pi, 8.0),
     (np.pi, 8.0, np.pi / 2, 2.0),   # negative corner tap in the up filter: forward falls back, adjoint folds
