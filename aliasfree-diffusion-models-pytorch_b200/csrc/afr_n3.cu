@@ -679,25 +679,29 @@ up3_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int H, 
     }
 }
 
-// down-like: thread = 4 output columns; input rows 2i-1, 2i, 2i+1, columns 2j-1 .. 2j+7
-template <typename T>
-__device__ __forceinline__ void load9(const T *plane, int row, int H, int W, int c0, bool has_l,
-                                      float (&v)[9])
+// down-like: thread = V output columns (4, or 8 for bf16 so that a thread still moves 128-bit
+// vectors both ways); input rows 2i-1, 2i, 2i+1, columns 2j-1 .. 2j+2V-1
+template <typename T, int V>
+__device__ __forceinline__ void load_down_row(const T *plane, int row, int H, int W, int c0, bool has_l,
+                                              float (&v)[2 * V + 1])
 {
     if (row < 0 || row >= H) {
 #pragma unroll
-        for (int c = 0; c < 9; ++c) v[c] = 0.f;
+        for (int c = 0; c < 2 * V + 1; ++c) v[c] = 0.f;
         return;
     }
     const T *p = plane + (long)row * W + c0;
-    float w[8];
-    ld8(p, w);
     v[0] = has_l ? ld1(p - 1) : 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) v[c + 1] = w[c];
+    for (int h = 0; h < V / 4; ++h) {
+        float w[8];
+        ld8(p + 8 * h, w);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[8 * h + c + 1] = w[c];
+    }
 }
 
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 down3_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, int W, int Ho,
              int Wo, int strips, int nseg, int R, const __grid_constant__ Taps3 k)
@@ -708,19 +712,19 @@ down3_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, 
     const int s = (int)(idx % strips);
     const int seg = (int)((idx / strips) % nseg);
     const long p = idx / per_plane;
-    const int j = 4 * s, i0 = seg * R, i1 = min(Ho, i0 + R);
+    const int j = V * s, i0 = seg * R, i1 = min(Ho, i0 + R);
     const T *plane = in + p * (long)H * W;
     T *dst = out + p * (long)Ho * Wo + j;
     const bool has_l = (j > 0);
 
-    float vp[9], ve[9], vo[9];
-    load9(plane, 2 * i0 - 1, H, W, 2 * j, has_l, vp);
+    float vp[2 * V + 1], ve[2 * V + 1], vo[2 * V + 1];
+    load_down_row<T, V>(plane, 2 * i0 - 1, H, W, 2 * j, has_l, vp);
     for (int i = i0; i < i1; ++i) {
-        load9(plane, 2 * i, H, W, 2 * j, has_l, ve);
-        load9(plane, 2 * i + 1, H, W, 2 * j, has_l, vo);
-        float o[4];
+        load_down_row<T, V>(plane, 2 * i, H, W, 2 * j, has_l, ve);
+        load_down_row<T, V>(plane, 2 * i + 1, H, W, 2 * j, has_l, vo);
+        float o[V];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < V; ++q) {
             float acc = k.k[0][0] * vp[2 * q];
             acc = fmaf(k.k[0][1], vp[2 * q + 1], acc);
             acc = fmaf(k.k[0][2], vp[2 * q + 2], acc);
@@ -732,9 +736,16 @@ down3_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, 
             acc = fmaf(k.k[2][2], vo[2 * q + 2], acc);
             o[q] = acc;
         }
-        st4(dst + (long)i * Wo, make_float4(o[0], o[1], o[2], o[3]));
+        if (V == 8) {
+            float o8[8];
 #pragma unroll
-        for (int c = 0; c < 9; ++c) vp[c] = vo[c];
+            for (int q = 0; q < 8; ++q) o8[q] = o[q % V];
+            st8(dst + (long)i * Wo, o8);
+        } else {
+            st4(dst + (long)i * Wo, make_float4(o[0], o[1], o[2], o[3]));
+        }
+#pragma unroll
+        for (int c = 0; c < 2 * V + 1; ++c) vp[c] = vo[c];
     }
 }
 
@@ -1025,16 +1036,22 @@ cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, c
                          int dtype, cudaStream_t s)
 {
     const int Ho = (H + 1) / 2, Wo = W / 2;
-    const int strips = Wo / 4, R = pick_rows(Ho), nseg = (Ho + R - 1) / R;
+    // bf16: 8 outputs per thread when the row width and the bases allow 128-bit vectors both ways
+    const bool wide = dtype == AFR_BF16 && (Wo % 8) == 0 && aligned_to(in, 16) && aligned_to(out, 16);
+    const int V = wide ? 8 : 4;
+    const int strips = Wo / V, R = pick_rows(Ho), nseg = (Ho + R - 1) / R;
     const long total = planes * (long)strips * nseg;
     const long grid = (total + 255) / 256;
     if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
     if (dtype == AFR_F32)
-        down3_kernel<float><<<(unsigned)grid, 256, 0, s>>>((const float *)in, (float *)out, planes,
-                                                           H, W, Ho, Wo, strips, nseg, R, k);
+        down3_kernel<float, 4><<<(unsigned)grid, 256, 0, s>>>((const float *)in, (float *)out, planes,
+                                                              H, W, Ho, Wo, strips, nseg, R, k);
+    else if (wide)
+        down3_kernel<bf16, 8><<<(unsigned)grid, 256, 0, s>>>((const bf16 *)in, (bf16 *)out, planes, H,
+                                                             W, Ho, Wo, strips, nseg, R, k);
     else
-        down3_kernel<bf16><<<(unsigned)grid, 256, 0, s>>>((const bf16 *)in, (bf16 *)out, planes, H,
-                                                          W, Ho, Wo, strips, nseg, R, k);
+        down3_kernel<bf16, 4><<<(unsigned)grid, 256, 0, s>>>((const bf16 *)in, (bf16 *)out, planes, H,
+                                                             W, Ho, Wo, strips, nseg, R, k);
     return cudaGetLastError();
 }
 
