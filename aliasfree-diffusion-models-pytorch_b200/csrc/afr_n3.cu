@@ -614,7 +614,10 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
         TileRows<T, false> sd{ds + toff, nullptr, pitch, r0, H, Affine{0.f, 0.f, 0.f, 0.f}};
         mbar_wait(&full[k & 1], (k >> 1) & 1);
         if (k == 0) strip_begin<kBwd, KT>(sx, sd, r0, S0);
-        for (int i = r0; i < r0 + cfg.R; i += 2) {   // R is even: register roles return to S0
+        // R is even: register roles return to S0.  The last chunk stops after the segment's last row
+        // (rounded up to a pair of steps) instead of walking rows nobody needs.
+        const int rend = min(r0 + cfg.R, seg_hi + ((seg_hi - r0) & 1));
+        for (int i = r0; i < rend; i += 2) {
             strip_step<kBwd>(sx, sd, dst, W, i, valid && i >= seg_lo && i < seg_hi, first_col, own0, K, S0, S1);
             strip_step<kBwd>(sx, sd, dst, W, i + 1, valid && i + 1 >= seg_lo && i + 1 < seg_hi, first_col, own0, K,
                              S1, S0);
@@ -892,11 +895,17 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
                 const size_t bytes = (size_t)(c.Tw + 2 * (16 / es)) * (c.R + 1) * c.P * es;
                 c.tile_bytes = (int)((bytes + 127) / 128 * 128);
                 if ((size_t)c.tile_bytes * nin * 2 <= ring_budget_bytes()) {
-                    // row segments: only when whole-plane streaming leaves the GPU under-filled
-                    // (< ~20 warps per SM); each extra segment costs one dry step
-                    const long warps = (planes * c.tiles_x * c.strips + 31) / 32;
+                    // row segments: when whole-plane streaming gives fewer than ~2.5 waves of CTAs the SMs
+                    // finish unevenly (long-lived CTAs, no second wave to even things out); each extra
+                    // segment costs one dry step, so segments stay at least 2R rows tall
+                    const long ctas = (planes + c.P - 1) / c.P * c.tiles_x;
+                    long resident = (long)(220 * 1024) / ((long)c.tile_bytes * nin * 2);
+                    resident = resident < 1 ? 1 : resident;
+                    if (resident > 65536 / (100 * t)) resident = 65536 / (100 * t);
+                    if (resident > 32) resident = 32;
                     c.nsegs = 1;
-                    while (warps * c.nsegs < 20L * 148 && H / (c.nsegs * 2) >= 2 * c.R && c.nsegs < 16) c.nsegs *= 2;
+                    while (2 * ctas * c.nsegs < 5 * 148 * resident && H / (c.nsegs * 2) >= 2 * c.R && c.nsegs < 16) c.nsegs *= 2;
+                    if (const char *e = getenv("AFR_NSEGS")) c.nsegs = atoi(e) > 0 ? atoi(e) : 1;   // tuning runs
                     c.Hs = ((H + c.nsegs - 1) / c.nsegs + c.R - 1) / c.R * c.R;
                     c.nsegs = (H + c.Hs - 1) / c.Hs;
                     *threads = t; *cfg = c;

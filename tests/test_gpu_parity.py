@@ -498,3 +498,42 @@ def test_extreme_inputs(afr, oracle):
                         assert relmax(dxh[b, c], want_dx[b, c]) <= FP32_TOL, (path, float(mag[b, c, 0, 0]))
         finally:
             afr.set_path("auto")
+
+
+def test_fuzz_shapes_all_ops(afr, oracle):
+    """Seeded random shapes / filter sizes / dtypes / residual through whatever kernel AUTO selects
+    (symmetric and general N == 3, compile-time-N strips, runtime-N backstop), forward and adjoint
+    against the oracle.  Small planes so that the oracle stays fast."""
+    rng = np.random.default_rng(2024)
+    seen = set()
+    for case in range(70):
+        n = int(rng.choice([1, 2, 3, 3, 3, 4, 5, 6, 6, 7, 8, 9]))
+        B, C = int(rng.integers(1, 4)), int(rng.integers(1, 6))
+        H = int(rng.integers(1, 41))
+        W = int(rng.choice([4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 48, 64, 72, 132, 136, 7, 10, 33]))
+        sym = bool(rng.integers(0, 2))
+        ku = oracle.lowpass_taps(float(rng.uniform(0.3, 1.0) * np.pi), n, float(rng.uniform(0, 4)))
+        kd = oracle.lowpass_taps(float(rng.uniform(0.3, 1.0) * np.pi), n, None)
+        if not sym:
+            ku = ku + 0.02 * rng.standard_normal(ku.shape)
+            kd = kd + 0.02 * rng.standard_normal(kd.shape)
+        ku, kd = ku.astype(np.float32), kd.astype(np.float32)
+        x, r, dy = (rng.standard_normal((B, C, H, W)).astype(np.float32) for _ in range(3))
+        use_res = bool(rng.integers(0, 2))
+        xt, rt = dev(x, grad=True), dev(r, grad=True)
+        y = afr.filtered_gelu(xt, ku, kd, residual=rt if use_res else None)
+        seen.add(afr.last_kernel())
+        xin = x + r if use_res else x
+        tag = (case, n, (B, C, H, W), sym, use_res, afr.last_kernel())
+        assert relmax(host(y), oracle.filtered_gelu(xin, ku, kd)) <= FP32_TOL, tag
+        (gx,) = torch.autograd.grad(y, xt, dev(dy))
+        assert relmax(host(gx), oracle.filtered_gelu_bwd(xin, dy, ku, kd)) <= FP32_TOL, tag
+        u = afr.up2x(xt, ku)
+        assert relmax(host(u), oracle.up2x(x, ku)) <= FP32_TOL, tag
+        d = afr.down2x(xt, kd)
+        assert relmax(host(d), oracle.down2x(x, kd)) <= FP32_TOL, tag
+        if W % 8 == 0:
+            xb = dev(x, torch.bfloat16)
+            yb = afr.filtered_gelu(xb, ku, kd)
+            assert relmax(host(yb), oracle.filtered_gelu(host(xb), ku, kd)) <= BF16_TOL, tag
+    assert {"fgelu3_tma_kernel<sym>", "fgelu3_tma_kernel", "fgelu_strip_kernel", "fgelu_generic_kernel"} <= seen, seen
