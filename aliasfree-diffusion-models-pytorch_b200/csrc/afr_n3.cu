@@ -768,6 +768,14 @@ bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dt
 
 static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *threads, struct TileCfg *cfg);
 
+// tuning knobs read once per process (0 = unset)
+static int env_int(const char *name)
+{
+    static const int cta = []() { const char *e = getenv("AFR_CTA_THREADS"); return e ? atoi(e) : 0; }();
+    static const int nsg = []() { const char *e = getenv("AFR_NSEGS"); return e ? atoi(e) : 0; }();
+    return name[4] == 'C' ? cta : nsg;
+}
+
 static int tma_min_width()
 {
     static int v = []() { const char *e = getenv("AFR_TMA_MIN_W"); int w = e ? atoi(e) : 8; return w < 4 ? 4 : w; }();
@@ -882,7 +890,7 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
     // 128-thread CTAs unless that leaves fewer than ~6 CTAs per SM: long-lived streaming CTAs
     // need a few waves to balance, so small batches of large planes use smaller CTAs
     int th = 128;
-    if (const char *e = getenv("AFR_CTA_THREADS")) th = atoi(e);   // tuning runs
+    if (env_int("AFR_CTA_THREADS") > 0) th = env_int("AFR_CTA_THREADS");   // tuning runs
     while (th > 32 && th > c.strips && (planes * c.tiles_x * c.strips) / th < 6 * 148) th /= 2;
     if (th < c.strips) th = c.strips;
     if (th > 128) return false;
@@ -905,7 +913,7 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
                     if (resident > 32) resident = 32;
                     c.nsegs = 1;
                     while (2 * ctas * c.nsegs < 5 * 148 * resident && H / (c.nsegs * 2) >= 2 * c.R && c.nsegs < 16) c.nsegs *= 2;
-                    if (const char *e = getenv("AFR_NSEGS")) c.nsegs = atoi(e) > 0 ? atoi(e) : 1;   // tuning runs
+                    if (env_int("AFR_NSEGS") > 0) c.nsegs = env_int("AFR_NSEGS");   // tuning runs
                     c.Hs = ((H + c.nsegs - 1) / c.nsegs + c.R - 1) / c.R * c.R;
                     c.nsegs = (H + c.Hs - 1) / c.Hs;
                     *threads = t; *cfg = c;
