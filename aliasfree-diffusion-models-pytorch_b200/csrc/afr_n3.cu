@@ -203,8 +203,8 @@ struct StepK {             // general-tap kernels
 };
 
 template <bool kBwd, class SX, class SD, typename TO>
-__device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__restrict__ out, int W, int i,
-                                           bool store, bool first_col, bool own0, const StepK &K,
+__device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__restrict__ out_row, int i,
+                                           bool store, bool first_col, bool any0, bool own0, const StepK &K,
                                            const RowSet &A, RowSet &B)
 {
     const Taps3 &kU = K.kU, &kG = K.kG, &kB = K.kB;
@@ -221,7 +221,7 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
         up_odd_cols<1>(da, db, kG, mo);
         act_cols_1_8<true>(ue, me);
         act_cols_1_8<true>(uo, mo);
-        if (own0) {
+        if (any0 && own0) {      // any0 is warp-uniform: the common shapes skip with one uniform branch
             up_even_cols<0>(xa, kU, ue);
             up_odd_cols<0>(xa, xb, kU, uo);
             up_even_cols<0>(da, kG, me);
@@ -233,15 +233,15 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
         up_odd_cols<1>(xa, xb, kU, mo);
         act_cols_1_8<false>(me, me);
         act_cols_1_8<false>(mo, mo);
-        if (own0) {
+        if (any0 && own0) {      // any0 is warp-uniform: the common shapes skip with one uniform branch
             up_even_cols<0>(xa, kU, me);
             up_odd_cols<0>(xa, xb, kU, mo);
             act_col0_pair<false>(me, mo, me, mo);
         }
     }
     const float le = __shfl_up_sync(0xffffffffu, me[8], 1), lo = __shfl_up_sync(0xffffffffu, mo[8], 1);
-    if (!own0) { me[0] = le; mo[0] = lo; }
-    if (first_col) { me[0] = 0.f; mo[0] = 0.f; }
+    if (first_col) { me[0] = 0.f; mo[0] = 0.f; }             // own0 and first_col exclude each other (j > 0 vs j == 0)
+    if (!(own0 || first_col)) { me[0] = le; mo[0] = lo; }
     float o[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -256,7 +256,7 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
         acc = fmaf(kB.k[2][2], mo[2 * q + 2], acc);
         o[q] = acc;
     }
-    if (store) st4(out + (long)i * W, make_float4(o[0], o[1], o[2], o[3]));
+    if (store) st4(out_row, make_float4(o[0], o[1], o[2], o[3]));
 }
 
 // The same step for D4-symmetric taps [[a,b,a],[b',c,b'],[a,b,a]] (every filter circularLowpassKernel
@@ -316,8 +316,8 @@ __device__ __forceinline__ void sym_sums(const float (&xa)[6], const float (&ha)
 }
 
 template <bool kBwd, class SX, class SD, typename TO>
-__device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__restrict__ out, int W, int i,
-                                           bool store, bool first_col, bool own0, const SymK &K,
+__device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__restrict__ out_row, int i,
+                                           bool store, bool first_col, bool any0, bool own0, const SymK &K,
                                            const RowSet &A, RowSet &B)
 {
     sx.load(i + 1, B.x);
@@ -328,6 +328,7 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
         if (kBwd) B.hd[c] = B.d[c] + B.d[c + 1];
     }
     float me[9], mo[9];
+    float c0e = 0.f, c0o = 0.f;      // column 0 when it is not the left neighbour's: 0 at a plane edge, else own
     if (kBwd) {
         float ue[9], uo[9];
         sym_sums<1>(A.x, A.hx, B.x, B.hx, ue, uo);
@@ -339,12 +340,13 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
         }
         act_cols_1_8<true>(ue, me);
         act_cols_1_8<true>(uo, mo);
-        if (own0) {
+        if (any0 && own0) {      // any0 is warp-uniform: the common shapes skip with one uniform branch
             sym_sums<0>(A.x, A.hx, B.x, B.hx, ue, uo);
             sym_sums<0>(A.d, A.hd, B.d, B.hd, me, mo);
             ue[0] *= K.sw[PH_EO];
             uo[0] *= K.sw[PH_OO];
             act_col0_pair<true>(ue, uo, me, mo);
+            c0e = me[0]; c0o = mo[0];
         }
     } else {
         sym_sums<1>(A.x, A.hx, B.x, B.hx, me, mo);
@@ -356,14 +358,16 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
         gelu_hat_x2(mo[5], mo[7], K.p[PH_OE], K.p[PH_OE]);
         gelu_hat_x2(mo[2], mo[4], K.p[PH_OO], K.p[PH_OO]);
         gelu_hat_x2(mo[6], mo[8], K.p[PH_OO], K.p[PH_OO]);
-        if (own0) {
+        if (any0 && own0) {      // any0 is warp-uniform: the common shapes skip with one uniform branch
             sym_sums<0>(A.x, A.hx, B.x, B.hx, me, mo);
             gelu_hat_x2(me[0], mo[0], K.p[PH_EO], K.p[PH_OO]);
+            c0e = me[0]; c0o = mo[0];
         }
     }
     const float le = __shfl_up_sync(0xffffffffu, me[8], 1), lo = __shfl_up_sync(0xffffffffu, mo[8], 1);
-    if (!own0) { me[0] = le; mo[0] = lo; }
-    if (first_col) { me[0] = 0.f; mo[0] = 0.f; }
+    const bool take = !(own0 || first_col);                  // own0 and first_col exclude each other
+    me[0] = take ? le : c0e;
+    mo[0] = take ? lo : c0o;
     float o[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -374,7 +378,7 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
         acc = fmaf(K.dn[PH_EE], me[2 * q + 1], acc);
         o[q] = acc + ro;
     }
-    if (store) st4(out + (long)i * W, make_float4(o[0], o[1], o[2], o[3]));
+    if (store) st4(out_row, make_float4(o[0], o[1], o[2], o[3]));
 }
 
 template <class KT> struct IsSym { static constexpr bool value = false; };
@@ -419,7 +423,7 @@ __device__ __forceinline__ void strip_core(const SX &sx, const SD &sd, TO *__res
     clear_carry(S1);
     if (__any_sync(0xffffffffu, i0 > 0)) {
         strip_begin<kBwd, KT>(sx, sd, i0 - 1, S1);
-        strip_step<kBwd>(sx, sd, out, W, i0 - 1, false, first_col, own0, K, S1, S0);
+        strip_step<kBwd>(sx, sd, out, i0 - 1, false, first_col, true, own0, K, S1, S0);
     } else {
         strip_begin<kBwd, KT>(sx, sd, i0, S0);
     }
@@ -427,10 +431,10 @@ __device__ __forceinline__ void strip_core(const SX &sx, const SD &sd, TO *__res
     const int iend = i0 + R;
     int i = i0;
     for (; i + 1 < iend; i += 2) {
-        strip_step<kBwd>(sx, sd, out, W, i, valid && i < i1, first_col, own0, K, S0, S1);
-        strip_step<kBwd>(sx, sd, out, W, i + 1, valid && i + 1 < i1, first_col, own0, K, S1, S0);
+        strip_step<kBwd>(sx, sd, out + (long)i * W, i, valid && i < i1, first_col, true, own0, K, S0, S1);
+        strip_step<kBwd>(sx, sd, out + (long)(i + 1) * W, i + 1, valid && i + 1 < i1, first_col, true, own0, K, S1, S0);
     }
-    if (i < iend) strip_step<kBwd>(sx, sd, out, W, i, valid && i < i1, first_col, own0, K, S0, S1);
+    if (i < iend) strip_step<kBwd>(sx, sd, out + (long)i * W, i, valid && i < i1, first_col, true, own0, K, S0, S1);
 }
 
 // ---------------------------------------------------------------------------------
@@ -530,6 +534,8 @@ struct TileCfg {
     int tiles_x;               // column tiles per plane
     int ghost;                 // planes wider than one tile: leading strips of every tile that only
                                // feed the column-0 shuffle of their right neighbour (never stored)
+    int own0_any;              // some lane's left neighbour strip is not lane-1 (W > 128 without ghosts, or a strip
+                               // count that does not divide a warp); 0 lets every step skip the recompute branch
     int nsegs, Hs;             // row segments per plane (blockIdx.y) and their height
     int tile_bytes;            // bytes of one staged box, rounded up to 128
 };
@@ -594,7 +600,8 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     const bool first_col = (j == 0);
     // with ghost strips every real strip has its left neighbour in lane-1; otherwise lane 0 of a
     // warp that does not start a plane row recomputes column 0 itself
-    const bool own0 = (cfg.ghost == 0) && (j > 0) && (s == 0 || (threadIdx.x & 31) == 0);
+    const bool any0 = cfg.own0_any != 0;
+    const bool own0 = any0 && (cfg.ghost == 0) && (j > 0) && (s == 0 || (threadIdx.x & 31) == 0);
     const int toff = pl * rows * pitch + HALO + 4 * s;
     T *dst = out + (p0 + pl) * (long)H * W + (valid ? j : 0);
     const Affine aff = make_affine(kAff ? scale : nullptr, shift, p0 + pl, p0 + pl < planes, j, W);
@@ -610,17 +617,32 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
         const T *rs = reinterpret_cast<const T *>(base + (kRes ? cfg.tile_bytes : 0));
         const T *ds = reinterpret_cast<const T *>(base + (kRes ? 2 : 1) * cfg.tile_bytes);
         const int r0 = istart + k * cfg.R;
-        TileRows<T, kRes, kAff> sx{xs + toff, rs + toff, pitch, r0, H, aff};
-        TileRows<T, false> sd{ds + toff, nullptr, pitch, r0, H, Affine{0.f, 0.f, 0.f, 0.f}};
         mbar_wait(&full[k & 1], (k >> 1) & 1);
-        if (k == 0) strip_begin<kBwd, KT>(sx, sd, r0, S0);
+        if (k == 0) {
+            TileRows<T, kRes, kAff> sx{xs + toff, rs + toff, pitch, r0, H, aff};
+            TileRows<T, false> sd{ds + toff, nullptr, pitch, r0, H, Affine{0.f, 0.f, 0.f, 0.f}};
+            strip_begin<kBwd, KT>(sx, sd, r0, S0);
+        }
         // R is even: register roles return to S0.  The last chunk stops after the segment's last row
-        // (rounded up to a pair of steps) instead of walking rows nobody needs.
+        // (rounded up to a pair of steps) instead of walking rows nobody needs.  Row pointers (staged
+        // rows i+1 / i+2 and the output row) are carried instead of being rebuilt from the row index.
         const int rend = min(r0 + cfg.R, seg_hi + ((seg_hi - r0) & 1));
+        const T *xr = xs + toff + pitch, *rr = rs + toff + pitch, *dr = ds + toff + pitch;
+        T *orow = dst + (long)r0 * W;
         for (int i = r0; i < rend; i += 2) {
-            strip_step<kBwd>(sx, sd, dst, W, i, valid && i >= seg_lo && i < seg_hi, first_col, own0, K, S0, S1);
-            strip_step<kBwd>(sx, sd, dst, W, i + 1, valid && i + 1 >= seg_lo && i + 1 < seg_hi, first_col, own0, K,
-                             S1, S0);
+            {
+                TileRows<T, kRes, kAff> sx{xr, rr, pitch, i + 1, H, aff};
+                TileRows<T, false> sd{dr, nullptr, pitch, i + 1, H, Affine{0.f, 0.f, 0.f, 0.f}};
+                strip_step<kBwd>(sx, sd, orow, i, valid && i >= seg_lo && i < seg_hi, first_col, any0, own0, K, S0, S1);
+            }
+            {
+                TileRows<T, kRes, kAff> sx{xr + pitch, rr + pitch, pitch, i + 2, H, aff};
+                TileRows<T, false> sd{dr + pitch, nullptr, pitch, i + 2, H, Affine{0.f, 0.f, 0.f, 0.f}};
+                strip_step<kBwd>(sx, sd, orow + W, i + 1, valid && i + 1 >= seg_lo && i + 1 < seg_hi, first_col, any0, own0, K,
+                                 S1, S0);
+            }
+            xr += 2 * pitch; rr += 2 * pitch; dr += 2 * pitch;
+            orow += 2 * W;
         }
         __syncthreads();                            // stage k & 1 fully consumed
         if (threadIdx.x == 0 && k + 2 < nchunks) issue(k + 2);
@@ -916,6 +938,7 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
                     if (env_int("AFR_NSEGS") > 0) c.nsegs = env_int("AFR_NSEGS");   // tuning runs
                     c.Hs = ((H + c.nsegs - 1) / c.nsegs + c.R - 1) / c.R * c.R;
                     c.nsegs = (H + c.Hs - 1) / c.Hs;
+                    c.own0_any = (c.ghost == 0) && (c.tiles_x > 1 || (32 % c.strips) != 0);
                     *threads = t; *cfg = c;
                     return true;
                 }
