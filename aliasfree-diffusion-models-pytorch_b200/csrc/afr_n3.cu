@@ -716,14 +716,14 @@ __device__ __forceinline__ void load_down_row(const T *plane, int row, int H, in
         return;
     }
     const T *p = plane + (long)row * W + c0;
-    v[0] = has_l ? ld1(p - 1) : 0.f;
 #pragma unroll
-    for (int h = 0; h < V / 4; ++h) {
+    for (int h = 0; h < V / 4; ++h) {          // the wide loads go first (issue order = arrival order)
         float w[8];
         ld8(p + 8 * h, w);
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[8 * h + c + 1] = w[c];
     }
+    v[0] = has_l ? ld1(p - 1) : 0.f;
 }
 
 template <typename T, int V>
