@@ -286,6 +286,8 @@ upn_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int H, 
         for (int r = 0; r + 1 < G::NR; ++r)
 #pragma unroll
             for (int c = 0; c < G::NC; ++c) w[r][c] = w[r + 1][c];
+        // bf16 input: pull the row after next into L2 (+18 %; costs 15 % with fp32 input, so bf16 only)
+        if (sizeof(TI) == 2 && i + G::rhi() + 2 < H) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (long)(i + G::rhi() + 2) * W + j));
         load_window_row<TI, false, G::clo(), G::chi()>(src, nullptr, i + G::rhi(), H, W, j, w[G::NR - 1]);
         float e[8], o[8];
         UpRow<G, N, 0>::run(w, t, e);
@@ -320,6 +322,11 @@ downn_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, 
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[k][q] = 0.f;
     for (int i = i0 - (K - 1); i < i1; ++i) {
+        if (sizeof(T) == 2 && 2 * i + C0 + 5 < H && 2 * i + C0 + 4 >= 0) {   // bf16 only, as in down3_kernel
+            const T *pf = plane + (long)(2 * i + C0 + 4) * W + 2 * j;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + W));
+        }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int Y = 2 * i + C0 + e;
