@@ -45,9 +45,13 @@ typedef enum {
     AFR_ERR_UNSUPPORTED = 7    /* e.g. resampling factor != 2 */
 } afr_status;
 
-/* Path selection for the N==3 kernels (testing / benchmarking aid). */
+/* Kernel-family selection (testing / benchmarking aid; production code leaves AUTO).
+ * AUTO: N == 3 -> TMA-staged row-streaming kernel when the shape allows, else the direct
+ * register-strip kernel (both in their symmetric-tap variant when the filters are
+ * D4-symmetric, as every circularLowpassKernel filter is); both filters N x N with
+ * N in {2,4,5,6,7,8} -> compile-time-N strip kernels; anything else -> runtime-N kernels. */
 typedef enum {
-    AFR_PATH_AUTO = 0,      /* TMA-staged tiles when the shape allows, else direct */
+    AFR_PATH_AUTO = 0,
     AFR_PATH_DIRECT = 1,    /* register-strip kernel reading global memory directly */
     AFR_PATH_TMA = 2,       /* force the TMA tile kernel (error if shape unsupported) */
     AFR_PATH_GENERIC = 3,   /* force the runtime-N shared-memory kernels */
