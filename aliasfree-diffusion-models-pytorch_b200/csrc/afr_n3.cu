@@ -800,12 +800,16 @@ bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dt
 
 static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *threads, struct TileCfg *cfg);
 
-// tuning knobs read once per process (0 = unset)
-static int env_int(const char *name)
+// tuning knobs, read once per process (0 = unset): CTA size and row segments of the TMA kernel
+static int env_cta_threads()
 {
-    static const int cta = []() { const char *e = getenv("AFR_CTA_THREADS"); return e ? atoi(e) : 0; }();
-    static const int nsg = []() { const char *e = getenv("AFR_NSEGS"); return e ? atoi(e) : 0; }();
-    return name[4] == 'C' ? cta : nsg;
+    static const int v = []() { const char *e = getenv("AFR_CTA_THREADS"); return e ? atoi(e) : 0; }();
+    return v;
+}
+static int env_nsegs()
+{
+    static const int v = []() { const char *e = getenv("AFR_NSEGS"); return e ? atoi(e) : 0; }();
+    return v;
 }
 
 static int tma_min_width()
@@ -922,7 +926,7 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
     // 128-thread CTAs unless that leaves fewer than ~6 CTAs per SM: long-lived streaming CTAs
     // need a few waves to balance, so small batches of large planes use smaller CTAs
     int th = 128;
-    if (env_int("AFR_CTA_THREADS") > 0) th = env_int("AFR_CTA_THREADS");   // tuning runs
+    if (env_cta_threads() > 0) th = env_cta_threads();   // tuning runs
     while (th > 32 && th > c.strips && (planes * c.tiles_x * c.strips) / th < 6 * 148) th /= 2;
     if (th < c.strips) th = c.strips;
     if (th > 128) return false;
@@ -945,7 +949,7 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
                     if (resident > 32) resident = 32;
                     c.nsegs = 1;
                     while (2 * ctas * c.nsegs < 5 * 148 * resident && H / (c.nsegs * 2) >= 2 * c.R && c.nsegs < 16) c.nsegs *= 2;
-                    if (env_int("AFR_NSEGS") > 0) c.nsegs = env_int("AFR_NSEGS");   // tuning runs
+                    if (env_nsegs() > 0) c.nsegs = env_nsegs();   // tuning runs
                     c.Hs = ((H + c.nsegs - 1) / c.nsegs + c.R - 1) / c.R * c.R;
                     c.nsegs = (H + c.Hs - 1) / c.Hs;
                     c.own0_any = (c.ghost == 0) && (c.tiles_x > 1 || (32 % c.strips) != 0);
@@ -978,12 +982,9 @@ static cudaError_t launch_tma(const void *x, const void *res, const void *dy, co
     const dim3 grid3((unsigned)grid, (unsigned)cfg.nsegs);
     const size_t smem = (size_t)cfg.tile_bytes * nin * 2;
     auto kern = fgelu3_tma_kernel<T, kBwd, kRes, kAff, KT>;
-    static bool attr_set = false;     // per instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e != cudaSuccess) { set_detail("cudaFuncSetAttribute(max dynamic smem) failed"); return e; }
-        attr_set = true;
-    }
+    // once per instantiation and process (thread-safe static initialisation)
+    static const cudaError_t attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (attr_err != cudaSuccess) { set_detail("cudaFuncSetAttribute(max dynamic smem) failed"); return attr_err; }
     kern<<<grid3, threads, smem, s>>>(mx, mres, mdy, scale, shift, (T *)out, planes, H, W, cfg, K);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
