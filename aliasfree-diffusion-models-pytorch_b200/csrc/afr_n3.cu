@@ -27,6 +27,7 @@
 //           zero padding, mbarrier complete_tx), threads read rows from the staged chunk.
 #include <cuda.h>
 #include <cstdlib>
+#include <type_traits>
 
 #include "afr_common.cuh"
 #include "afr_kernels.h"
@@ -629,21 +630,30 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
         const int rend = min(r0 + cfg.R, seg_hi + ((seg_hi - r0) & 1));
         const T *xr = xs + toff + pitch, *rr = rs + toff + pitch, *dr = ds + toff + pitch;
         T *orow = dst + (long)r0 * W;
-        for (int i = r0; i < rend; i += 2) {
-            {
-                TileRows<T, kRes, kAff> sx{xr, rr, pitch, i + 1, H, aff};
-                TileRows<T, false> sd{dr, nullptr, pitch, i + 1, H, Affine{0.f, 0.f, 0.f, 0.f}};
-                strip_step<kBwd>(sx, sd, orow, i, valid && i >= seg_lo && i < seg_hi, first_col, any0, own0, K, S0, S1);
+        // chunks that lie completely inside the segment (all but the first of a later segment and the
+        // last) store under the per-thread predicate alone: no row comparisons in the hot loop
+        auto walk = [&](auto inside) {
+            constexpr bool kInside = decltype(inside)::value;
+            for (int i = r0; i < rend; i += 2) {
+                {
+                    TileRows<T, kRes, kAff> sx{xr, rr, pitch, i + 1, H, aff};
+                    TileRows<T, false> sd{dr, nullptr, pitch, i + 1, H, Affine{0.f, 0.f, 0.f, 0.f}};
+                    strip_step<kBwd>(sx, sd, orow, i, kInside ? valid : (valid && i >= seg_lo && i < seg_hi), first_col,
+                                     any0, own0, K, S0, S1);
+                }
+                {
+                    TileRows<T, kRes, kAff> sx{xr + pitch, rr + pitch, pitch, i + 2, H, aff};
+                    TileRows<T, false> sd{dr + pitch, nullptr, pitch, i + 2, H, Affine{0.f, 0.f, 0.f, 0.f}};
+                    strip_step<kBwd>(sx, sd, orow + W, i + 1,
+                                     kInside ? valid : (valid && i + 1 >= seg_lo && i + 1 < seg_hi), first_col, any0,
+                                     own0, K, S1, S0);
+                }
+                xr += 2 * pitch; rr += 2 * pitch; dr += 2 * pitch;
+                orow += 2 * W;
             }
-            {
-                TileRows<T, kRes, kAff> sx{xr + pitch, rr + pitch, pitch, i + 2, H, aff};
-                TileRows<T, false> sd{dr + pitch, nullptr, pitch, i + 2, H, Affine{0.f, 0.f, 0.f, 0.f}};
-                strip_step<kBwd>(sx, sd, orow + W, i + 1, valid && i + 1 >= seg_lo && i + 1 < seg_hi, first_col, any0, own0, K,
-                                 S1, S0);
-            }
-            xr += 2 * pitch; rr += 2 * pitch; dr += 2 * pitch;
-            orow += 2 * W;
-        }
+        };
+        if (r0 >= seg_lo && r0 + cfg.R <= seg_hi) walk(std::true_type{});
+        else walk(std::false_type{});
         __syncthreads();                            // stage k & 1 fully consumed
         if (threadIdx.x == 0 && k + 2 < nchunks) issue(k + 2);
     }
