@@ -279,7 +279,7 @@ static int fused_common(const void *x, const void *residual, const void *dy, voi
         const bool tma_ok = n3_fgelu_tma_supported(planes, H, W, ptrs, 4, dtype, 1 + (residual ? 1 : 0) + (bwd ? 1 : 0));
         if (path == AFR_PATH_TMA && !tma_ok)
             return fail(AFR_ERR_UNSUPPORTED, "TMA path forced but shape/alignment not eligible (H=%d W=%d)", H, W);
-        const bool use_tma = (path == AFR_PATH_TMA) || (path == AFR_PATH_AUTO && tma_ok);
+        const bool use_tma = (path == AFR_PATH_TMA) || (path == AFR_PATH_AUTO && tma_ok && !n3_prefers_plane_kernel(H, W, bwd));
         Taps3 kU, kG, kB;
         set_taps3(kU, taps_up, false);
         if (bwd)                       // the adjoint kernels evaluate gelu' in w = kappa * u

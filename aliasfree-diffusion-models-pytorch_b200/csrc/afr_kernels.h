@@ -34,6 +34,7 @@ cudaError_t stripn_down_like(const void *in, void *out, long planes, int H, int 
 // afr_n3.cu -- N == 3 register-strip kernels (direct and TMA-staged)
 // All take stage taps already arranged for the stencil they run (see afr_api.cu).
 bool n3_fgelu_supported(int H, int W, const void *const *ptrs, int nptrs, int dtype);
+bool n3_prefers_plane_kernel(int H, int W, bool bwd);
 bool n3_fgelu_tma_supported(long planes, int H, int W, const void *const *ptrs, int nptrs, int dtype,
                             int n_inputs);
 cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, const float *scale, const float *shift,

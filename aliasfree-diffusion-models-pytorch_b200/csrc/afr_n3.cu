@@ -474,6 +474,98 @@ fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T
 }
 
 // ---------------------------------------------------------------------------------
+// 4x4 and 8x8 planes (the innermost UNet levels): whole planes in registers
+// ---------------------------------------------------------------------------------
+// Everything the general direct kernel decides at run time is a constant here: a plane is one
+// (4x4) or two (8x8) strips wide, there are no row segments, the steps are fully unrolled, and all
+// rows of every input are requested up front (one 128-bit load per row and tensor, plus the one
+// neighbour column of the other strip for 8x8), so a thread exposes one memory latency per plane.
+// 8x8: the two strips of a plane sit in an even/odd lane pair, column 0 of the odd strip comes
+// from the even lane by shuffle.  (The 8x8 adjoint stays on the TMA kernel: two tensors of nine
+// rows do not fit a reasonable register budget.)
+template <int HH>
+struct RegRows {
+    float v[HH + 1][6];                             // rows 0..HH-1 and the zero row HH; columns -1 .. 4
+    __device__ __forceinline__ void load(int row, float (&o)[6]) const
+    {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) o[c] = v[row][c];
+    }
+};
+
+template <typename T, bool kRes, int HH>
+__device__ __forceinline__ void load_plane_rows(const T *__restrict__ xp, const T *__restrict__ rp, int s,
+                                                float a, float b, bool affine, RegRows<HH> &R)
+{
+    constexpr int WW = HH;                          // square planes
+#pragma unroll
+    for (int r = 0; r < HH; ++r) {
+        const T *row = xp + r * WW + 4 * s;
+        float4 c4 = ld4(row);
+        float nb = 0.f;                             // 8x8: the column next to the strip inside the plane
+        if (WW == 8) nb = ld1(s == 0 ? row + 4 : row - 1);
+        if (kRes) {
+            const T *rrow = rp + r * WW + 4 * s;
+            const float4 q4 = ld4(rrow);
+            if (affine) { c4.x = fmaf(c4.x, a, b); c4.y = fmaf(c4.y, a, b); c4.z = fmaf(c4.z, a, b); c4.w = fmaf(c4.w, a, b); nb = fmaf(nb, a, b); }
+            c4.x += q4.x; c4.y += q4.y; c4.z += q4.z; c4.w += q4.w;
+            if (WW == 8) nb += ld1(s == 0 ? rrow + 4 : rrow - 1);
+        } else if (affine) {
+            c4.x = fmaf(c4.x, a, b); c4.y = fmaf(c4.y, a, b); c4.z = fmaf(c4.z, a, b); c4.w = fmaf(c4.w, a, b); nb = fmaf(nb, a, b);
+        }
+        R.v[r][1] = c4.x; R.v[r][2] = c4.y; R.v[r][3] = c4.z; R.v[r][4] = c4.w;
+        R.v[r][0] = (WW == 8 && s == 1) ? nb : 0.f;
+        R.v[r][5] = (WW == 8 && s == 0) ? nb : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) R.v[HH][c] = 0.f;
+}
+
+template <bool kBwd, class KT, int HH, int I = 0>
+struct PlaneSteps {
+    template <typename T>
+    static __device__ __forceinline__ void run(const RegRows<HH> &sx, const RegRows<HH> &sd, T *op, bool valid,
+                                               bool first_col, const KT &K, RowSet &A, RowSet &B)
+    {
+        strip_step<kBwd>(sx, sd, op + I * HH, I, valid, first_col, false, false, K, A, B);
+        PlaneSteps<kBwd, KT, HH, I + 1>::run(sx, sd, op, valid, first_col, K, B, A);
+    }
+};
+template <bool kBwd, class KT, int HH>
+struct PlaneSteps<kBwd, KT, HH, HH> {
+    template <typename T>
+    static __device__ __forceinline__ void run(const RegRows<HH> &, const RegRows<HH> &, T *, bool, bool, const KT &,
+                                               RowSet &, RowSet &) {}
+};
+
+template <typename T, bool kBwd, bool kRes, bool kAff, class KT, int HH>
+__global__ void __launch_bounds__(128)
+fgelu3_plane_kernel(const T *__restrict__ x, const T *__restrict__ res, const T *__restrict__ dy,
+                    const float *__restrict__ scale, const float *__restrict__ shift,
+                    T *__restrict__ out, long planes, const __grid_constant__ KT K)
+{
+    constexpr int STRIPS = HH / 4, HW = HH * HH;
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    long p = idx / STRIPS;
+    const int s = (int)(idx % STRIPS);
+    const bool valid = p < planes;
+    if (STRIPS == 1 && !valid) return;              // 4x4 has no shuffles: idle lanes may leave
+    if (!valid) p = 0;                              // 8x8: idle lanes shadow plane 0, stores off
+    const T *xp = x + p * HW, *rp = kRes ? res + p * HW : nullptr, *dp = kBwd ? dy + p * HW : nullptr;
+    RegRows<HH> sx, sd;
+    float a = 1.f, b = 0.f;
+    if (kAff) { a = __ldg(scale + p); b = __ldg(shift + p); }
+    load_plane_rows<T, kRes, HH>(xp, rp, s, a, b, kAff, sx);
+    if (kBwd) load_plane_rows<T, false, HH>(dp, nullptr, s, 1.f, 0.f, false, sd);
+    RowSet S0, S1;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { S0.d[c] = 0.f; S1.d[c] = 0.f; }
+    clear_carry(S0);
+    strip_begin<kBwd, KT>(sx, sd, 0, S0);
+    PlaneSteps<kBwd, KT, HH>::run(sx, sd, out + p * HW + 4 * s, valid, s == 0, K, S0, S1);
+}
+
+// ---------------------------------------------------------------------------------
 // TMA-staged kernel
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -828,6 +920,19 @@ static int tma_min_width()
     return v;
 }
 
+static bool plane_kernels_disabled()   // AFR_NO_PLANE=1: A/B runs of the general kernels on 4x4 / 8x8 planes
+{
+    static const bool v = []() { const char *e = getenv("AFR_NO_PLANE"); return e && atoi(e) != 0; }();
+    return v;
+}
+
+// AUTO sends these shapes to the whole-plane register kernels (launch_direct) even though TMA could stage them
+bool n3_prefers_plane_kernel(int H, int W, bool bwd)
+{
+    if (plane_kernels_disabled()) return false;
+    return (H == 4 && W == 4) || (H == 8 && W == 8 && !bwd);
+}
+
 bool n3_fgelu_tma_supported(long planes, int H, int W, const void *const *ptrs, int nptrs, int dtype,
                             int n_inputs)
 {
@@ -888,14 +993,31 @@ static bool make_plane_map(CUtensorMap *m, const void *base, long planes, int H,
 
 static inline int pick_rows(int H) { return H < 8 ? H : 8; }
 
+
 template <typename T, bool kBwd, bool kRes, bool kAff, class KT>
 static cudaError_t launch_direct(const void *x, const void *res, const void *dy, const float *scale,
                                  const float *shift, void *out, long planes, int H, int W,
                                  const KT &K, cudaStream_t s)
 {
+    const int block = 128;
+    if (H == 4 && W == 4 && !plane_kernels_disabled()) {          // one thread per plane, everything unrolled
+        const long g4 = (planes + block - 1) / block;
+        if (g4 > 0x7fffffffL) { set_detail("too many planes"); return cudaErrorInvalidConfiguration; }
+        fgelu3_plane_kernel<T, kBwd, kRes, kAff, KT, 4><<<(unsigned)g4, block, 0, s>>>(
+            (const T *)x, (const T *)res, (const T *)dy, scale, shift, (T *)out, planes, K);
+        return cudaGetLastError();
+    }
+    if constexpr (!kBwd) {
+        if (H == 8 && W == 8 && !plane_kernels_disabled()) {      // a lane pair per plane
+            const long g8 = (2 * planes + block - 1) / block;
+            if (g8 > 0x7fffffffL) { set_detail("too many planes"); return cudaErrorInvalidConfiguration; }
+            fgelu3_plane_kernel<T, false, kRes, kAff, KT, 8><<<(unsigned)g8, block, 0, s>>>(
+                (const T *)x, (const T *)res, nullptr, scale, shift, (T *)out, planes, K);
+            return cudaGetLastError();
+        }
+    }
     const int strips = W / 4, R = pick_rows(H), nseg = (H + R - 1) / R;
     const long total = planes * (long)strips * nseg;
-    const int block = 128;
     const long grid = (total + block - 1) / block;
     if (total >= 0x7fffffffL) { set_detail("tensor too large for the direct kernel's 32-bit indexing"); return cudaErrorInvalidConfiguration; }
     fgelu3_direct_kernel<T, kBwd, kRes, kAff, KT><<<(unsigned)grid, block, 0, s>>>(

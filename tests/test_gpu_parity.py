@@ -310,6 +310,11 @@ def test_kernel_selection(afr):
     assert afr.last_kernel() == "fgelu3_tma_kernel<sym>"          # D4-symmetric taps: folded-tap variant
     afr.filtered_gelu(torch.randn(2, 2, 4, 4, device="cuda"), k, k)
     assert afr.last_kernel() == "fgelu3_direct_kernel<sym>"
+    afr.filtered_gelu(torch.randn(2, 2, 8, 8, device="cuda"), k, k)
+    assert afr.last_kernel() == "fgelu3_direct_kernel<sym>"       # 8x8 forward: whole-plane register kernel
+    afr.ops._fgelu_bwd(torch.randn(2, 2, 8, 8, device="cuda"), None, torch.randn(2, 2, 8, 8, device="cuda"),
+                       afr.Taps(k), afr.Taps(k))
+    assert afr.last_kernel() == "fgelu3_tma_kernel<sym>"          # 8x8 adjoint: TMA kernel
     ka = k.clone(); ka[0, 1] += 0.01                                # asymmetric taps: general 3x3 variant
     afr.filtered_gelu(torch.randn(2, 2, 32, 32, device="cuda"), ka, k)
     assert afr.last_kernel() == "fgelu3_tma_kernel"
