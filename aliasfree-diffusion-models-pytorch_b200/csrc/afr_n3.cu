@@ -481,8 +481,8 @@ fgelu3_direct_kernel(const T *__restrict__ x, const T *__restrict__ res, const T
 // rows of every input are requested up front (one 128-bit load per row and tensor, plus the one
 // neighbour column of the other strip for 8x8), so a thread exposes one memory latency per plane.
 // 8x8: the two strips of a plane sit in an even/odd lane pair, column 0 of the odd strip comes
-// from the even lane by shuffle.  (The 8x8 adjoint stays on the TMA kernel: two tensors of nine
-// rows do not fit a reasonable register budget.)
+// from the even lane by shuffle.  (The 8x8 adjoint reads its rows on demand instead: two tensors
+// of nine rows do not fit a reasonable register budget.)
 template <int HH>
 struct RegRows {
     float v[HH + 1][6];                             // rows 0..HH-1 and the zero row HH; columns -1 .. 4
@@ -521,10 +521,39 @@ __device__ __forceinline__ void load_plane_rows(const T *__restrict__ xp, const 
     for (int c = 0; c < 6; ++c) R.v[HH][c] = 0.f;
 }
 
+// The same rows read when a step asks for them (the 8x8 adjoint: two tensors of nine rows are too many
+// registers).  Row indices are compile-time constants after unrolling, so there are still no bounds
+// checks; the rows were requested with an L1 prefetch up front.
+template <typename T, bool kRes, int HH>
+struct LazyRows {
+    const T *xp, *rp;
+    int s;
+    __device__ __forceinline__ void load(int row, float (&o)[6]) const
+    {
+        if (row >= HH) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) o[c] = 0.f;
+            return;
+        }
+        const T *p = xp + row * HH + 4 * s;
+        float4 c4 = ld4(p);
+        float nb = (HH == 8) ? ld1(s == 0 ? p + 4 : p - 1) : 0.f;
+        if (kRes) {
+            const T *q = rp + row * HH + 4 * s;
+            const float4 q4 = ld4(q);
+            c4.x += q4.x; c4.y += q4.y; c4.z += q4.z; c4.w += q4.w;
+            if (HH == 8) nb += ld1(s == 0 ? q + 4 : q - 1);
+        }
+        o[1] = c4.x; o[2] = c4.y; o[3] = c4.z; o[4] = c4.w;
+        o[0] = (HH == 8 && s == 1) ? nb : 0.f;
+        o[5] = (HH == 8 && s == 0) ? nb : 0.f;
+    }
+};
+
 template <bool kBwd, class KT, int HH, int I = 0>
 struct PlaneSteps {
-    template <typename T>
-    static __device__ __forceinline__ void run(const RegRows<HH> &sx, const RegRows<HH> &sd, T *op, bool valid,
+    template <class SX, class SD, typename T>
+    static __device__ __forceinline__ void run(const SX &sx, const SD &sd, T *op, bool valid,
                                                bool first_col, const KT &K, RowSet &A, RowSet &B)
     {
         strip_step<kBwd>(sx, sd, op + I * HH, I, valid, first_col, false, false, K, A, B);
@@ -533,9 +562,8 @@ struct PlaneSteps {
 };
 template <bool kBwd, class KT, int HH>
 struct PlaneSteps<kBwd, KT, HH, HH> {
-    template <typename T>
-    static __device__ __forceinline__ void run(const RegRows<HH> &, const RegRows<HH> &, T *, bool, bool, const KT &,
-                                               RowSet &, RowSet &) {}
+    template <class SX, class SD, typename T>
+    static __device__ __forceinline__ void run(const SX &, const SD &, T *, bool, bool, const KT &, RowSet &, RowSet &) {}
 };
 
 template <typename T, bool kBwd, bool kRes, bool kAff, class KT, int HH>
@@ -552,17 +580,30 @@ fgelu3_plane_kernel(const T *__restrict__ x, const T *__restrict__ res, const T 
     if (STRIPS == 1 && !valid) return;              // 4x4 has no shuffles: idle lanes may leave
     if (!valid) p = 0;                              // 8x8: idle lanes shadow plane 0, stores off
     const T *xp = x + p * HW, *rp = kRes ? res + p * HW : nullptr, *dp = kBwd ? dy + p * HW : nullptr;
-    RegRows<HH> sx, sd;
-    float a = 1.f, b = 0.f;
-    if (kAff) { a = __ldg(scale + p); b = __ldg(shift + p); }
-    load_plane_rows<T, kRes, HH>(xp, rp, s, a, b, kAff, sx);
-    if (kBwd) load_plane_rows<T, false, HH>(dp, nullptr, s, 1.f, 0.f, false, sd);
     RowSet S0, S1;
 #pragma unroll
     for (int c = 0; c < 6; ++c) { S0.d[c] = 0.f; S1.d[c] = 0.f; }
     clear_carry(S0);
-    strip_begin<kBwd, KT>(sx, sd, 0, S0);
-    PlaneSteps<kBwd, KT, HH>::run(sx, sd, out + p * HW + 4 * s, valid, s == 0, K, S0, S1);
+    if constexpr (kBwd && HH == 8) {                // rows on demand (see LazyRows)
+#pragma unroll
+        for (int r = 0; r < HH; ++r) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(xp + r * HH + 4 * s));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(dp + r * HH + 4 * s));
+            if (kRes) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + r * HH + 4 * s));
+        }
+        const LazyRows<T, kRes, HH> sx{xp, rp, s};
+        const LazyRows<T, false, HH> sd{dp, nullptr, s};
+        strip_begin<kBwd, KT>(sx, sd, 0, S0);
+        PlaneSteps<kBwd, KT, HH>::run(sx, sd, out + p * HW + 4 * s, valid, s == 0, K, S0, S1);
+    } else {
+        RegRows<HH> sx, sd;
+        float a = 1.f, b = 0.f;
+        if (kAff) { a = __ldg(scale + p); b = __ldg(shift + p); }
+        load_plane_rows<T, kRes, HH>(xp, rp, s, a, b, kAff, sx);
+        if (kBwd) load_plane_rows<T, false, HH>(dp, nullptr, s, 1.f, 0.f, false, sd);
+        strip_begin<kBwd, KT>(sx, sd, 0, S0);
+        PlaneSteps<kBwd, KT, HH>::run(sx, sd, out + p * HW + 4 * s, valid, s == 0, K, S0, S1);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -930,7 +971,8 @@ static bool plane_kernels_disabled()   // AFR_NO_PLANE=1: A/B runs of the genera
 bool n3_prefers_plane_kernel(int H, int W, bool bwd)
 {
     if (plane_kernels_disabled()) return false;
-    return (H == 4 && W == 4) || (H == 8 && W == 8 && !bwd);
+    (void)bwd;
+    return (H == 4 && W == 4) || (H == 8 && W == 8);
 }
 
 bool n3_fgelu_tma_supported(long planes, int H, int W, const void *const *ptrs, int nptrs, int dtype,
@@ -1007,14 +1049,12 @@ static cudaError_t launch_direct(const void *x, const void *res, const void *dy,
             (const T *)x, (const T *)res, (const T *)dy, scale, shift, (T *)out, planes, K);
         return cudaGetLastError();
     }
-    if constexpr (!kBwd) {
-        if (H == 8 && W == 8 && !plane_kernels_disabled()) {      // a lane pair per plane
-            const long g8 = (2 * planes + block - 1) / block;
-            if (g8 > 0x7fffffffL) { set_detail("too many planes"); return cudaErrorInvalidConfiguration; }
-            fgelu3_plane_kernel<T, false, kRes, kAff, KT, 8><<<(unsigned)g8, block, 0, s>>>(
-                (const T *)x, (const T *)res, nullptr, scale, shift, (T *)out, planes, K);
-            return cudaGetLastError();
-        }
+    if (H == 8 && W == 8 && !plane_kernels_disabled()) {          // a lane pair per plane
+        const long g8 = (2 * planes + block - 1) / block;
+        if (g8 > 0x7fffffffL) { set_detail("too many planes"); return cudaErrorInvalidConfiguration; }
+        fgelu3_plane_kernel<T, kBwd, kRes, kAff, KT, 8><<<(unsigned)g8, block, 0, s>>>(
+            (const T *)x, (const T *)res, (const T *)dy, scale, shift, (T *)out, planes, K);
+        return cudaGetLastError();
     }
     const int strips = W / 4, R = pick_rows(H), nseg = (H + R - 1) / R;
     const long total = planes * (long)strips * nseg;
