@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libafr_b200.so")
 SOURCES = ["afr_api.cu", "afr_generic.cu", "afr_n3.cu", "afr_stripn.cu", "afr_rotate.cu"]
 HEADERS = ["afr_common.cuh", "afr_kernels.h", os.path.join("..", "..", "include", "afr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "--threads", "0"]
 
 _lock = threading.Lock()
 _lib = None
