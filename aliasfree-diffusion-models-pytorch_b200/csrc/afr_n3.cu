@@ -849,6 +849,50 @@ up3_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int H, 
     }
 }
 
+// Short planes (H = 4 or 8, the innermost UNet levels): the same arithmetic with the plane height a
+// compile-time constant -- every row of the strip is requested before the first one is used (one
+// exposed memory latency per strip instead of one per row) and the row loop is fully unrolled.
+template <typename TI, typename TO, int HH>
+__global__ void __launch_bounds__(256)
+up3_short_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int W, int strips,
+                 const __grid_constant__ Taps3 k)
+{
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (idx >= planes * strips) return;
+    const int s = (int)(idx % strips);
+    const long p = idx / strips;
+    const int j = 4 * s, W2 = 2 * W;
+    const TI *src = in + p * (long)HH * W + j;
+    TO *dst = out + p * 4L * HH * W + 2 * j;
+    const bool has_r = (j + 4 < W);
+    float x[HH + 1][5];
+#pragma unroll
+    for (int r = 0; r < HH; ++r) {
+        const float4 c = ld4(src + r * W);
+        x[r][0] = c.x; x[r][1] = c.y; x[r][2] = c.z; x[r][3] = c.w;
+        x[r][4] = has_r ? ld1(src + r * W + 4) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 5; ++c) x[HH][c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < HH; ++i) {
+        float e[8], o[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            e[2 * c] = k.k[1][1] * x[i][c];
+            e[2 * c + 1] = fmaf(k.k[1][2], x[i][c + 1], k.k[1][0] * x[i][c]);
+            o[2 * c] = fmaf(k.k[2][1], x[i + 1][c], k.k[0][1] * x[i][c]);
+            float t = k.k[0][0] * x[i][c];
+            t = fmaf(k.k[0][2], x[i][c + 1], t);
+            t = fmaf(k.k[2][0], x[i + 1][c], t);
+            o[2 * c + 1] = fmaf(k.k[2][2], x[i + 1][c + 1], t);
+        }
+        TO *r0 = dst + (long)(2 * i) * W2;
+        st8(r0, e);
+        st8(r0 + W2, o);
+    }
+}
+
 // down-like: thread = V output columns (4, or 8 for bf16 so that a thread still moves 128-bit
 // vectors both ways); input rows 2i-1, 2i, 2i+1, columns 2j-1 .. 2j+2V-1
 template <typename T, int V>
@@ -924,6 +968,45 @@ down3_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, 
         }
 #pragma unroll
         for (int c = 0; c < 2 * V + 1; ++c) vp[c] = vo[c];
+    }
+}
+
+// H = 8 input rows -> 4 output rows
+template <typename T, int HH>
+__global__ void __launch_bounds__(256)
+down3_short_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int W, int Wo, int strips,
+                   const __grid_constant__ Taps3 k)
+{
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (idx >= planes * strips) return;
+    const int s = (int)(idx % strips);
+    const long p = idx / strips;
+    const int j = 4 * s;
+    const T *plane = in + p * (long)HH * W;
+    T *dst = out + p * (long)(HH / 2) * Wo + j;
+    const bool has_l = (j > 0);
+    float v[HH + 1][9];                             // v[r + 1] = input row r; v[0] = row -1 (zero padding)
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[0][c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < HH; ++r) load_down_row<T, 4>(plane, r, HH, W, 2 * j, has_l, v[r + 1]);
+#pragma unroll
+    for (int i = 0; i < HH / 2; ++i) {
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float acc = k.k[0][0] * v[2 * i][2 * q];
+            acc = fmaf(k.k[0][1], v[2 * i][2 * q + 1], acc);
+            acc = fmaf(k.k[0][2], v[2 * i][2 * q + 2], acc);
+            acc = fmaf(k.k[1][0], v[2 * i + 1][2 * q], acc);
+            acc = fmaf(k.k[1][1], v[2 * i + 1][2 * q + 1], acc);
+            acc = fmaf(k.k[1][2], v[2 * i + 1][2 * q + 2], acc);
+            acc = fmaf(k.k[2][0], v[2 * i + 2][2 * q], acc);
+            acc = fmaf(k.k[2][1], v[2 * i + 2][2 * q + 1], acc);
+            acc = fmaf(k.k[2][2], v[2 * i + 2][2 * q + 2], acc);
+            o[q] = acc;
+        }
+        st4(dst + (long)i * Wo, make_float4(o[0], o[1], o[2], o[3]));
     }
 }
 
@@ -1238,9 +1321,19 @@ cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, con
     const long total = planes * (long)strips * nseg;
     const long grid = (total + 255) / 256;
     if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
-#define AFR_UP(TI, TO)                                                                        \
-    up3_kernel<TI, TO><<<(unsigned)grid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, H, W, \
-                                                      strips, nseg, R, k)
+    // bf16 input only: with fp32 input the up-front loads are 15-60 % slower than the row loop (measured)
+    const bool short_plane = (H == 4 || H == 8) && in_dtype == AFR_BF16 && !plane_kernels_disabled();
+    const long sgrid = (planes * strips + 255) / 256;
+#define AFR_UP(TI, TO)                                                                                       \
+    do {                                                                                                     \
+        if (short_plane && H == 4)                                                                           \
+            up3_short_kernel<TI, TO, 4><<<(unsigned)sgrid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, W, strips, k); \
+        else if (short_plane)                                                                                \
+            up3_short_kernel<TI, TO, 8><<<(unsigned)sgrid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, W, strips, k); \
+        else                                                                                                 \
+            up3_kernel<TI, TO><<<(unsigned)grid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, H, W,        \
+                                                              strips, nseg, R, k);                           \
+    } while (0)
     if (in_dtype == AFR_F32 && out_dtype == AFR_F32) AFR_UP(float, float);
     else if (in_dtype == AFR_BF16 && out_dtype == AFR_BF16) AFR_UP(bf16, bf16);
     else if (in_dtype == AFR_BF16 && out_dtype == AFR_F32) AFR_UP(bf16, float);
@@ -1266,6 +1359,13 @@ cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, c
     const long total = planes * (long)strips * nseg;
     const long grid = (total + 255) / 256;
     if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    if (H == 8 && dtype == AFR_BF16 && !plane_kernels_disabled()) {   // short bf16 planes: all rows up front, unrolled (+16 %; fp32: no gain)
+        const int sstrips = Wo / 4;
+        const long sgrid = (planes * sstrips + 255) / 256;
+        if (sgrid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+        down3_short_kernel<bf16, 8><<<(unsigned)sgrid, 256, 0, s>>>((const bf16 *)in, (bf16 *)out, planes, W, Wo, sstrips, k);
+        return cudaGetLastError();
+    }
     if (dtype == AFR_F32)
         down3_kernel<float, 4><<<(unsigned)grid, 256, 0, s>>>((const float *)in, (float *)out, planes,
                                                               H, W, Ho, Wo, strips, nseg, R, k);
