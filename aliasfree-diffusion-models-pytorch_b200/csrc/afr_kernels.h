@@ -2,9 +2,27 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "afr_common.cuh"
 
 namespace afr {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (kernel, device) pair: applied once per
+// device the calling thread launches on (`done` is a per-kernel bit mask indexed by device ordinal;
+// a lost race just sets the attribute twice).
+template <class F>
+inline cudaError_t ensure_dyn_smem(F kern, std::atomic<unsigned long long> &done, int bytes)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
 
 // Extra context for afr_last_error(), set by launchers when a step fails (thread local).
 void set_detail(const char *fmt, ...);

@@ -1237,9 +1237,9 @@ static cudaError_t launch_tma(const void *x, const void *res, const void *dy, co
     const dim3 grid3((unsigned)grid, (unsigned)cfg.nsegs);
     const size_t smem = (size_t)cfg.tile_bytes * nin * 2;
     auto kern = fgelu3_tma_kernel<T, kBwd, kRes, kAff, KT>;
-    // once per instantiation and process (thread-safe static initialisation)
-    static const cudaError_t attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (attr_err != cudaSuccess) { set_detail("cudaFuncSetAttribute(max dynamic smem) failed"); return attr_err; }
+    // once per instantiation and device
+    static std::atomic<unsigned long long> attr_done{0};
+    if (cudaError_t ae = ensure_dyn_smem(kern, attr_done, 100 * 1024)) { set_detail("cudaFuncSetAttribute(max dynamic smem) failed"); return ae; }
     kern<<<grid3, threads, smem, s>>>(mx, mres, mdy, scale, shift, (T *)out, planes, H, W, cfg, K);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)

@@ -94,13 +94,8 @@ cudaError_t rotate_periodic_cubic(const float *x, float *y, long planes, int H, 
     const double ch = 0.5 * (H - 1), cw = 0.5 * (W - 1);
     const double off_r = ch - (cs * ch + sn * cw), off_c = cw - (-sn * ch + cs * cw);
     const size_t smem = sizeof(double) * (size_t)H * (W | 1);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    if (cudaError_t e = ensure_dyn_smem(rotate_kernel, attr_done, 200 * 1024)) return e;
     if (planes > 0x7fffffffL) return cudaErrorInvalidConfiguration;
     const int threads = H * W >= 4096 ? 256 : 128;
     rotate_kernel<<<(unsigned)planes, threads, smem, s>>>(x, y, H, W, cs, sn, off_r, off_c);

@@ -10,6 +10,7 @@ sample, revert, rotate_2d_matrix, sample_shift).  Differences, all invisible in 
   * no per-step host tensors are created (the reference builds ``t`` on the CPU each step, :362).
 """
 import logging
+import weakref
 
 import numpy as np
 import torch
@@ -34,12 +35,16 @@ class Diffusion:
     def prepare_noise_schedule(self):
         return torch.linspace(self.beta_start, self.beta_end, self.noise_steps)
 
-    def noise_images(self, x, t, generator=None):
-        """q-sample (ddpm_models.py:317-321)."""
+    def noise_images(self, x, t, generator=None, noise=None):
+        """q-sample (ddpm_models.py:317-321).  ``noise`` injects the draw (tests, exact replays)."""
         sa = torch.sqrt(self.alpha_hat[t])[:, None, None, None]
         sb = torch.sqrt(1 - self.alpha_hat[t])[:, None, None, None]
-        eps = torch.randn(x.shape, dtype=x.dtype, device=x.device, generator=generator) \
-            if generator is not None else torch.randn_like(x)
+        if noise is not None:
+            eps = noise
+        elif generator is not None:
+            eps = torch.randn(x.shape, dtype=x.dtype, device=x.device, generator=generator)
+        else:
+            eps = torch.randn_like(x)
         return sa * x + sb * eps, eps
 
     def sample_timesteps(self, n, generator=None):
@@ -121,15 +126,34 @@ class Diffusion:
         graph._afr_keepalive = (table, t_long)                        # tensors the graph reads
         return graph, step
 
+    def prepare_graph(self, model, n, image_channels, theta=None):
+        """Capture (once) and cache the reverse-step graph for this (model, batch shape, theta): later
+        ``sample(..., cuda_graph=True)`` calls with the same arguments replay it without re-capturing.
+        The graph reads the model's parameters in place, so training between calls is fine; a model
+        whose parameter STORAGE is replaced (``.to()``, ``load_state_dict`` keeps storage and is fine)
+        needs ``clear_graphs()``."""
+        key = (id(model), int(n), int(image_channels), None if theta is None else float(theta))
+        cache = self.__dict__.setdefault("_graphs", {})
+        hit = cache.get(key)
+        if hit is None or hit[3]() is not model:            # id() of a collected model may be reused
+            x = torch.zeros((n, image_channels, self.img_size, self.img_size), device=self.device)
+            graph, step = self.capture_reverse_step(model, x, theta)
+            hit = cache[key] = (graph, step, x, weakref.ref(model))
+        return hit[:3]
+
+    def clear_graphs(self):
+        self.__dict__.pop("_graphs", None)
+
     def _graphed_loop(self, model, n, image_channels, theta, keep, x_init, generator):
-        x = self._initial(n, image_channels, x_init, generator)
-        graph, _ = self.capture_reverse_step(model, x, theta)
+        graph, step, x = self.prepare_graph(model, n, image_channels, theta)
+        x.copy_(self._initial(n, image_channels, x_init, generator))
+        step.fill_(self.noise_steps - 1)
         kept = []
         for i in reversed(range(1, self.noise_steps)):
             graph.replay()
             if keep and i % 100 == 0:
                 kept.append(x.clone())
-        return x, kept
+        return x.clone(), kept
 
     @staticmethod
     def _to_u8(x):

@@ -39,17 +39,23 @@ def _require(x, name="x"):
 
 
 class Taps:
-    """Host copy of an N x N filter, kept alive next to its ctypes pointer."""
-    __slots__ = ("t", "n", "ptr")
+    """Host copy of an N x N filter.  Only the tensor is state: the pointer handed to the C ABI is taken
+    from it at launch time, so a ``Taps`` (and any module caching one) can be deep-copied and pickled --
+    the reference's ``copy.deepcopy(model)`` EMA pattern and whole-model ``torch.save`` keep working."""
+    __slots__ = ("t", "n")
 
     def __init__(self, filt):
         if isinstance(filt, Taps):
-            self.t, self.n, self.ptr = filt.t, filt.n, filt.ptr
+            self.t, self.n = filt.t, filt.n
             return
         t = torch.as_tensor(filt).detach().to("cpu", torch.float32).contiguous()
         if t.dim() != 2 or t.shape[0] != t.shape[1]:
             raise ValueError("afr: filter must be N x N, got %s" % (tuple(t.shape),))
-        self.t, self.n, self.ptr = t, int(t.shape[0]), ctypes.c_void_p(t.data_ptr())
+        self.t, self.n = t, int(t.shape[0])
+
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.t.data_ptr())
 
 
 def _taps(filt):

@@ -108,12 +108,13 @@ class FlatGradAllReduce:
             self.flat.div_(self.world_size)
 
 
-def train_step(model, diffusion, optimizer, images, ddp=None, generator=None):
+def train_step(model, diffusion, optimizer, images, ddp=None, generator=None, noise=None):
     """Inner step of the reference ``train`` (modules/ddpm_utils.py:498-509): timesteps,
     q-sample, forward, MSE, backward, [grad all-reduce], AdamW.  Returns the loss tensor
-    (no host sync here; the reference's two ``loss.item()`` calls are the caller's business)."""
+    (no host sync here; the reference's two ``loss.item()`` calls are the caller's business).
+    ``noise`` replaces the q-sample draw (exact replays)."""
     t = diffusion.sample_timesteps(images.shape[0], generator=generator).to(images.device)
-    x_t, noise = diffusion.noise_images(images, t)
+    x_t, noise = diffusion.noise_images(images, t, noise=noise)
     pred = model(x_t, t)
     loss = torch.nn.functional.mse_loss(pred, noise)
     if ddp is not None:
@@ -134,23 +135,36 @@ class GraphedTrainStep:
     the eager step is launch-bound (~19 ms for ~4 ms of device work); replay removes that.
 
     The optimizer must be built with ``capturable=True``.  Timesteps are still drawn on the host
-    (reference: ``sample_timesteps`` is a CPU ``randint``) and copied into a static tensor."""
+    (reference: ``sample_timesteps`` is a CPU ``randint``) and copied into a static tensor.
 
-    def __init__(self, model, diffusion, optimizer, batch_shape, ddp=None, warmup=3):
+    The eager warm-up iterations that precede capture (lazy cuDNN / cuBLAS initialisation, optimizer
+    state allocation) run real optimizer steps on a dummy batch; parameters, buffers and every
+    optimizer state tensor are snapshotted before and restored IN PLACE afterwards (the graphs hold
+    their addresses), so constructing this object leaves the training state untouched.
+
+    ``static_noise=True`` makes the q-sample noise an input (``__call__(images, noise=...)``) instead
+    of a draw inside the graph -- used to replay an eager run exactly."""
+
+    def __init__(self, model, diffusion, optimizer, batch_shape, ddp=None, warmup=3, static_noise=False):
         self.model, self.diffusion, self.opt = model, diffusion, optimizer
         self.ddp = ddp if ddp is not None else FlatGradAllReduce(model)
         dev = next(model.parameters()).device
         self.images = torch.zeros(batch_shape, device=dev)
         self.t = torch.ones(batch_shape[0], dtype=torch.long, device=dev)
         self.loss = torch.zeros((), device=dev)
+        self.noise = torch.zeros(batch_shape, device=dev) if static_noise else None
 
         def fwd_bwd():
             self.ddp.zero_grad()
-            x_t, noise = diffusion.noise_images(self.images, self.t)
+            x_t, noise = diffusion.noise_images(self.images, self.t, noise=self.noise)
             loss = torch.nn.functional.mse_loss(model(x_t, self.t), noise)
             loss.backward()
             self.loss.copy_(loss.detach())
 
+        tensors = list(model.parameters()) + list(model.buffers())
+        saved = [t.detach().clone() for t in tensors]
+        saved_opt = {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                     for p, st in optimizer.state.items()}
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                       # eager warm-up: lazy inits, optimizer state
@@ -164,11 +178,57 @@ class GraphedTrainStep:
             fwd_bwd()
         with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
             optimizer.step()
+        with torch.no_grad():                               # undo the warm-up (capture executes nothing)
+            for t, s in zip(tensors, saved):
+                t.copy_(s)
+            for p, st in optimizer.state.items():
+                old = saved_opt.get(p)
+                for k, v in st.items():
+                    if not torch.is_tensor(v):
+                        if old is not None and k in old:
+                            st[k] = old[k]
+                    elif old is not None and k in old:
+                        v.copy_(old[k])
+                    else:
+                        v.zero_()                           # state created by the warm-up: a fresh optimizer starts at 0
+            self.ddp.zero_grad()
 
-    def __call__(self, images, generator=None):
+    def __call__(self, images, generator=None, noise=None):
+        tl = self.timeline
+        if tl is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
         self.images.copy_(images, non_blocking=True)
         self.t.copy_(self.diffusion.sample_timesteps(images.shape[0], generator=generator), non_blocking=True)
+        if self.noise is not None:
+            if noise is None:
+                raise ValueError("static_noise=True: pass the q-sample noise to every call")
+            self.noise.copy_(noise, non_blocking=True)
+        if tl is not None:
+            ev[1].record()
         self.g_fb.replay()
+        if tl is not None:
+            ev[2].record()
         self.ddp.sync()
+        if tl is not None:
+            ev[3].record()
         self.g_opt.replay()
+        if tl is not None:
+            ev[4].record()
+            tl.append(ev)
         return self.loss
+
+    timeline = None     # set to [] to collect per-step CUDA events (see ``timeline_ms``)
+
+    def timeline_ms(self):
+        """Mean device time per phase over the steps recorded since ``timeline = []`` (synchronises):
+        host timesteps + H2D copies | graph 1 (q-sample, forward, MSE, backward) | gradient all-reduce |
+        graph 2 (AdamW)."""
+        torch.cuda.synchronize()
+        names = ("inputs_h2d", "graph_fwd_bwd", "grad_allreduce", "graph_adamw")
+        if not self.timeline:
+            return {}
+        out = {n: sum(e[i].elapsed_time(e[i + 1]) for e in self.timeline) / len(self.timeline)
+               for i, n in enumerate(names)}
+        out["steps"] = len(self.timeline)
+        return out

@@ -10,8 +10,11 @@ filtered nonlinearity (up2x -> GELU -> low-pass -> down2x, forward) on the BASEL
 configs[4] microbench tensor, fp32, one batch per rank (weak scaling, no collective on
 the data path).  Extra keys: `roofline` (dominant kernel, timed live with CUDA events),
 `cpu_baseline` (oracle port on the host cores, bounded sample), `e2e` (same call through
-host buffers incl. H2D/D2H), `sweep` (other ops / dtypes / shapes) and `ddpm_v3`
-(Config-D reverse-diffusion steps: samples/sec at batch 4096 sharded over the ranks).
+host buffers incl. H2D/D2H), `sweep` (other ops / dtypes / shapes), `reference_eager_gpu` (the
+unmodified reference ops from baseline/_ref on the same GPU), `ddpm_v3` (configs[2]: ONE full
+999-step sharded Algorithm-1 run at batch 4096 -> samples/sec, plus the unmodified reference's UNet
+eager per reverse step), `train_v3` (configs[1], with a per-phase timeline), `ddp_grad_check`
+(sharded mean gradient through NCCL vs the whole-batch gradient), `config_e` and `config0`.
 """
 import argparse
 import json
@@ -157,17 +160,20 @@ def timed_loop(fn, steps, warmup, ws, per_step_events=False):
 
 
 # ---- reference arm: the CPU path on the host cores ----------------------------------------
-def _all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core it may run on."""
+def _all_host_threads(o):
+    """The CPU arm uses every core this process may run on.  torchrun exports OMP_NUM_THREADS=1 and libgomp
+    has read the environment long before this point (``import torch`` loads it), so the count is set
+    through the OpenMP API of the oracle library itself; returns the count now in force."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    os.environ["OMP_NUM_THREADS"] = str(n)
-    return n
+    got = o.set_threads(n)
+    assert got == n, f"CPU arm wanted {n} OpenMP threads, runtime reports {got}"
+    return got
 
 
 def cpu_reference(sample_b, min_seconds=10.0, max_reps=50):
-    _all_host_threads()
     from oracle import oracle as o
     o.build()
+    cores = _all_host_threads(o)
     k = o.lowpass_taps(np.pi / 2, 3, 2.0)
     C, H, W = WORKLOAD["C"], WORKLOAD["H"], WORKLOAD["W"]
     x = np.random.default_rng(0).standard_normal((sample_b, C, H, W)).astype(np.float32)
@@ -177,7 +183,7 @@ def cpu_reference(sample_b, min_seconds=10.0, max_reps=50):
     while len(times) < max_reps and (time.perf_counter() - t_all < min_seconds or len(times) < 3):
         t = time.perf_counter(); o.filtered_gelu(x, k, k); times.append(time.perf_counter() - t)
     nbytes = 2 * x.size * 4
-    return {"value": nbytes / float(np.median(times)) / 1e9, "unit": UNIT, "cores": o.num_threads(),
+    return {"value": nbytes / float(np.median(times)) / 1e9, "unit": UNIT, "cores": cores,
             "kind": "port", "reps": len(times),
             "sample": f"filtered_gelu fwd fp32 on [{sample_b},{C},{H},{W}] (1/{WORKLOAD['B'] // sample_b} of the GPU batch), "
                       f"median of {len(times)} runs, OpenMP over planes, host has {os.cpu_count()} logical cpus"}
@@ -187,9 +193,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    _all_host_threads()
     from oracle import oracle as o
     o.build()
+    cores = _all_host_threads(o)
     k = o.lowpass_taps(np.pi / 2, 3, 2.0)
     C, H, W = WORKLOAD["C"], WORKLOAD["H"], WORKLOAD["W"]
     sb = 32
@@ -207,24 +213,40 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "filtered_gelu_fwd fp32 [256,128,64,64] N=3 beta=2 omega=pi/2", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": o.num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
 
 
-# ---- the upstream GPU path: the reference's own PyTorch calls, eager, on this B200 ---------------
+# ---- the upstream GPU path: the UNMODIFIED reference, eager, on this B200 ---------------------------
+def load_reference():
+    """(filtrs, ddpm_utils, ddpm_models) of the unmodified reference (baseline/_ref on the GPU box,
+    installed by tools/install_ref.py), or None."""
+    try:
+        from baseline import ref_loader
+        return ref_loader.load() if ref_loader.available() else None
+    except Exception:
+        return None
+
+
 def reference_eager_gpu(afr):
-    """What the unmodified reference executes on a GPU (zero-stuff + depthwise F.conv2d + slice +
-    F.gelu, with its per-call filter upload), restated in baseline/torch_eager_reference.py because the
-    reference checkout is not on the GPU box.  Smaller batch than the headline: the unfused path
-    materialises three 4x-sized tensors.  Reported next to our kernel on the SAME tensor."""
-    from baseline import torch_eager_reference as tr
+    """What the unmodified reference executes on a GPU for one filtered nonlinearity: its own
+    ``custom_upsample`` -> ``F.gelu`` -> ``custom_downsample`` (modules/filtrs.py:71-94 called as in
+    modules/ddpm_utils.py:123-125), per-call filter upload included.  Smaller batch than the headline: the
+    unfused path materialises three 4x-sized tensors.  Reported next to our kernel on the SAME tensor."""
+    ref = load_reference()
+    if ref is None:
+        return {"unavailable": "no reference install (baseline/_ref) on this machine"}
+    rf = ref[0]
     B, C, H, W = 64, WORKLOAD["C"], WORKLOAD["H"], WORKLOAD["W"]
     x = torch.randn(B, C, H, W, device="cuda")
-    k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
+    k = rf.circularLowpassKernel(np.pi / 2, 3, 2)
     kt = afr.Taps(k)
     nbytes = 2 * x.numel() * 4
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+
+    def ref_op(v):
+        return rf.custom_downsample(torch.nn.functional.gelu(rf.custom_upsample(v, k)), k)
 
     def tm(fn, reps=5):
         fn(); torch.cuda.synchronize()
@@ -236,13 +258,35 @@ def reference_eager_gpu(afr):
             ts.append(a.elapsed_time(b))
         return float(np.median(ts))
 
+    out = {"shape": [B, C, H, W], "dtype": "f32"}
     with torch.no_grad():
-        ref_ms = tm(lambda: tr.filtered_gelu(x, k, k))
+        ref_ms = tm(lambda: ref_op(x))
         ours_ms = tm(lambda: afr.ops._fgelu_fwd(x, None, kt, kt))
-        err = float((tr.filtered_gelu(x, k, k) - afr.ops._fgelu_fwd(x, None, kt, kt)).abs().max())
-    return {"shape": [B, C, H, W], "dtype": "f32", "reference_eager_ms": ref_ms, "reference_eager_GBps": nbytes / ref_ms / 1e6,
-            "ours_ms": ours_ms, "ours_GBps": nbytes / ours_ms / 1e6, "speedup": ref_ms / ours_ms, "max_abs_diff": err,
-            "note": "algorithmic bytes 2*n*4 for both; reference = baseline/torch_eager_reference.py (the upstream eager op sequence)"}
+        err = float((ref_op(x) - afr.ops._fgelu_fwd(x, None, kt, kt)).abs().max())
+        out.update({"reference_eager_ms": ref_ms, "reference_eager_GBps": nbytes / ref_ms / 1e6, "ours_ms": ours_ms,
+                    "ours_GBps": nbytes / ours_ms / 1e6, "speedup": ref_ms / ours_ms, "max_abs_diff": err})
+        for name, rfn, ofn, nb in (
+                ("up2x", lambda: rf.custom_upsample(x, k), lambda: afr.ops._up_fwd(x, kt, torch.float32), 5 * x.numel() * 4),
+                ("down2x", lambda: rf.custom_downsample(x, k).contiguous(), lambda: afr.ops._down_fwd(x, kt), 1.25 * x.numel() * 4)):
+            r_ms, o_ms = tm(rfn), tm(ofn)
+            out[name] = {"reference_eager_ms": r_ms, "ours_ms": o_ms, "speedup": r_ms / o_ms,
+                         "ours_GBps": nb / o_ms / 1e6, "max_abs_diff": float((rfn() - ofn()).abs().max())}
+    xg = x[:16].clone().requires_grad_(True)
+    dy = torch.randn_like(xg)
+
+    def ref_fb():
+        xg.grad = None
+        ref_op(xg).backward(dy)
+
+    def ours_fb():
+        xg.grad = None
+        afr.filtered_gelu(xg, kt, kt).backward(dy)
+
+    r_ms, o_ms = tm(ref_fb), tm(ours_fb)
+    out["fwd_bwd_16"] = {"reference_eager_ms": r_ms, "ours_ms": o_ms, "speedup": r_ms / o_ms}
+    out["note"] = ("reference = the unmodified modules.filtrs functions from baseline/_ref called as ddpm_utils.py:123-125 does "
+                   "(algorithmic bytes 2*n*4 for both arms); up2x / down2x: the standalone functions; fwd_bwd_16: autograd on 16 images")
+    return out
 
 
 # ---- sweep over the other ops / shapes / dtypes (reported, not the headline) ------------------
@@ -298,44 +342,72 @@ def sweep(afr, quick, grid=False):
     return rows
 
 
-# ---- DDPM Config-D reverse steps (BASELINE configs[2]) ---------------------------------------------
-def ddpm_v3(afr, ws, rank, global_batch, steps, warmup):
+# ---- DDPM Config-D sampling (BASELINE configs[2]) ------------------------------------------------------
+def _wall_max(fn, ws):
+    """Run fn() between barrier + synchronize on both sides; wall seconds, max over ranks."""
+    barrier(ws)
+    t = time.perf_counter()
+    r = fn()
+    barrier(ws)
+    return max_over_ranks(time.perf_counter() - t, ws), r
+
+
+def ddpm_v3(afr, ws, rank, global_batch, steps, warmup, schedule):
+    """configs[2]: the FULL Algorithm-1 run -- ``parallel.sharded_sample`` of `global_batch` images,
+    `schedule` - 1 reverse steps (999), snapshots every 100 steps, uint8 conversion and the final
+    all-gather of the images -- timed as one call; samples/sec = global_batch / that time.  Secondary
+    figures: ms per reverse step (eager and graph replay), the same step under bf16 autocast, and the
+    UNMODIFIED reference (its UNet + its Diffusion.sample) eager on the same GPU at the per-rank batch."""
     from aliasfree_b200 import parallel
     torch.manual_seed(0)
     net = afr.UNet(c_in=3, c_out=3, image_size=32, f_settings=FS, variant=3).cuda().eval()
-    diff = afr.Diffusion(noise_steps=1000, img_size=32, device="cuda")
+    diff = afr.Diffusion(noise_steps=schedule, img_size=32, device="cuda")
     lo, hi = parallel.shard_bounds(global_batch, rank, ws)
     n = hi - lo
     x = torch.randn(n, 3, 32, 32, device="cuda")
-    state = {"i": 999}
+    state = {"i": schedule - 1}
 
     def eager_step():
         with torch.no_grad():
-            diff._reverse_step(net, x, state["i"], torch.randn_like(x))
+            diff._reverse_step(net, x, max(state["i"], 1), torch.randn_like(x))
         state["i"] -= 1
 
     l0 = afr.launch_count()
     eager_ms, _ = timed_loop(eager_step, steps, warmup, ws)
     eager_ms /= steps
     launches = (afr.launch_count() - l0) // (steps + warmup)
-    ms, mode = eager_ms, "eager"
-    graph = None
-    try:                                   # one reverse step captured in a CUDA graph and replayed
-        graph, step_dev = diff.capture_reverse_step(net, x)
-        step_dev.fill_(900)
-    except Exception as e:                 # capture is an optimisation, never a requirement
-        mode = "eager (graph capture failed: %s)" % repr(e)[:120]
-        graph = None
-    if all_ok(graph is not None, ws):
-        g_ms, _ = timed_loop(graph.replay, steps, warmup, ws)
-        g_ms /= steps
-        if g_ms < ms:
-            ms, mode = g_ms, "cuda_graph"
-    bf16_ms = None
+    out = {"global_batch": global_batch, "per_rank_batch": n, "schedule": schedule, "eager_ms_per_reverse_step": eager_ms,
+           "afr_launches_per_step": int(launches)}
+    del x
+    # the full run: graph captured once beforehand (reported separately), then ONE timed call
+    mode = "cuda_graph"
+    try:
+        t = time.perf_counter()
+        diff.prepare_graph(net, n, 3)
+        torch.cuda.synchronize()
+        out["graph_capture_s"] = time.perf_counter() - t
+        graph_ok = True
+    except Exception as e:
+        graph_ok, mode = False, "eager (graph capture failed: %s)" % repr(e)[:120]
+    use_graph = all_ok(graph_ok, ws)
+    if not use_graph and graph_ok:
+        mode = "eager (another rank could not capture)"
+    l0 = afr.launch_count()
+    full_s, res = _wall_max(lambda: parallel.sharded_sample(diff, net, global_batch, 3, seed=0, gather=(global_batch % ws == 0),
+                                                            cuda_graph=use_graph), ws)
+    x_u8, result_u8 = res
+    n_steps = schedule - 1
+    out.update({"samples_per_sec": global_batch / full_s, "full_run_s": full_s, "reverse_steps": n_steps, "mode": mode,
+                "ms_per_reverse_step": 1e3 * full_s / n_steps, "afr_launches_full_run": int(afr.launch_count() - l0),
+                "snapshots": int(result_u8.shape[0] // x_u8.shape[0]), "gathered_images": int(x_u8.shape[0]),
+                "output_dtype": str(x_u8.dtype).replace("torch.", ""),
+                "full": bool(schedule == 1000)})
+    del res, x_u8, result_u8
+    x = torch.randn(n, 3, 32, 32, device="cuda")
 
     def bf16_step():                       # extra data point, not the headline: same step under bf16 autocast
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-            diff._reverse_step(net, x, 500, torch.randn_like(x))
+            diff._reverse_step(net, x, schedule // 2, torch.randn_like(x))
 
     try:
         bf16_step()
@@ -344,13 +416,39 @@ def ddpm_v3(afr, ws, rank, global_batch, steps, warmup):
         bf16_ok = False
     if all_ok(bf16_ok, ws):
         bf16_total, _ = timed_loop(bf16_step, steps, warmup, ws)
-        bf16_ms = bf16_total / steps
-    return {"samples_per_sec": global_batch / (999 * ms / 1e3), "ms_per_reverse_step": ms, "mode": mode,
-            "eager_ms_per_reverse_step": eager_ms, "bf16_autocast_ms_per_reverse_step": bf16_ms,
-            "global_batch": global_batch, "per_rank_batch": n, "steps_timed": steps,
-            "note": "random-init UNet variant=3 c=3 32x32, fp32 (PyTorch default TF32 conv); "
-                    "samples/sec = batch / (999 x measured ms per reverse step); strong scaling over ranks",
-            "afr_launches_per_step": int(launches)}
+        out["bf16_autocast_ms_per_reverse_step"] = bf16_total / steps
+    del x
+    torch.cuda.empty_cache()
+    # the unmodified reference on the same GPU, same per-rank batch, through its own public API
+    ref = load_reference()
+    ref_ok = all_ok(ref is not None, ws)
+    if ref_ok:
+        try:
+            rm = ref[2]
+            rnet = rm.UNet(c_in=3, c_out=3, image_size=32, device="cuda", f_settings=FS, variant=3).cuda()
+            rnet.load_state_dict(net.state_dict(), strict=True)
+            k = 3
+            rdiff = rm.Diffusion(noise_steps=k + 1, img_size=32, device="cuda")
+            import logging
+            logging.disable(logging.INFO)
+            rdiff.sample(rnet, n=n, image_channels=3)                      # warm-up
+            ref_s, _ = _wall_max(lambda: rdiff.sample(rnet, n=n, image_channels=3), ws)
+            out["reference_eager_ms_per_reverse_step"] = 1e3 * ref_s / k
+            out["speedup_vs_reference_eager"] = out["reference_eager_ms_per_reverse_step"] / out["ms_per_reverse_step"]
+            out["reference_note"] = (f"unmodified modules.ddpm_models.UNet(variant=3) + Diffusion.sample from baseline/_ref, eager, "
+                                     f"{k} reverse steps at n={n} per rank incl. its uint8 conversion; same weights")
+            del rnet
+        except Exception as e:
+            out["reference_eager_ms_per_reverse_step"] = None
+            out["reference_note"] = "reference arm failed: " + repr(e)[:200]
+    else:
+        out["reference_eager_ms_per_reverse_step"] = None
+        out["reference_note"] = "no reference install (baseline/_ref) on this machine"
+    out["note"] = ("random-init UNet variant=3 c=3 32x32, fp32 (PyTorch default TF32 conv); samples/sec = global batch / wall time "
+                   "of ONE parallel.sharded_sample call (start noise from the seeded CPU draw + H2D, every reverse step, "
+                   "snapshots every 100 steps, uint8 conversion, all-gather), max over ranks; strong scaling over ranks; "
+                   "the reverse-step graph is captured before the timed call (graph_capture_s)")
+    return out
 
 
 _JSON_OUT = None
@@ -398,7 +496,7 @@ def train_v3(afr, ws, rank, global_batch, steps, warmup):
     launches = (afr.launch_count() - l0) // (steps + warmup)
     eager_ms = total_ms / steps
     ms, mode = eager_ms, "eager"
-    gstep = None
+    gstep, timeline = None, None
     try:                                   # same step, device work replayed from two CUDA graphs
         opt_g = torch.optim.AdamW(net.parameters(), lr=3e-4, capturable=True)
         gstep = parallel.GraphedTrainStep(net, diff, opt_g, tuple(dev.shape), ddp=ddp)
@@ -412,11 +510,152 @@ def train_v3(afr, ws, rank, global_batch, steps, warmup):
         g_total, _ = timed_loop(graphed, steps, warmup, ws)
         if g_total / steps < ms:
             ms, mode = g_total / steps, "cuda_graph"
+        gstep.timeline = []                # a second, instrumented pass: where the step's device time goes
+        for _ in range(steps):
+            graphed()
+        timeline = gstep.timeline_ms()
+        gstep.timeline = None
+        t = time.perf_counter()
+        for _ in range(steps):
+            diff.sample_timesteps(hi - lo)
+        timeline["host_randint_ms"] = 1e3 * (time.perf_counter() - t) / steps
+        timeline["sum_ms"] = sum(timeline[k] for k in ("inputs_h2d", "graph_fwd_bwd", "grad_allreduce", "graph_adamw"))
+        timeline["allreduce_bytes"] = int(ddp.flat.numel() * 4) if ws > 1 else 0
+    # the unmodified reference's train step on this GPU (its UNet, its Diffusion, the lines of train())
+    ref_ms, ref_note = None, "no reference install (baseline/_ref) on this machine"
+    ref = load_reference()
+    if all_ok(ref is not None, ws) and ws == 1:
+        try:
+            ru, rm = ref[1], ref[2]
+            rnet = rm.UNet(c_in=3, c_out=3, image_size=32, device="cuda", f_settings=FS, variant=3).cuda().train()
+            rdiff = rm.Diffusion(noise_steps=1000, img_size=32, device="cuda")
+            ropt = torch.optim.AdamW(rnet.parameters(), lr=3e-4)
+            mse = torch.nn.MSELoss()
+
+            def ref_step():                # modules/ddpm_utils.py:499-508, verbatim order of operations
+                images = host.to("cuda")
+                t = rdiff.sample_timesteps(images.shape[0]).to("cuda")
+                x_t, noise = rdiff.noise_images(images, t)
+                loss = mse(noise, rnet(x_t, t))
+                ropt.zero_grad()
+                loss.backward()
+                ropt.step()
+                return loss.item()
+
+            r_total, _ = timed_loop(ref_step, max(3, steps // 4), 2, ws)
+            ref_ms = r_total / max(3, steps // 4)
+            ref_note = "unmodified reference UNet(variant=3) + Diffusion from baseline/_ref, the inner-step lines of train(), eager, same batch"
+            del rnet, ropt
+        except Exception as e:
+            ref_note = "reference arm failed: " + repr(e)[:200]
+    elif ws > 1:
+        ref_note = "reference arm is single-device (it has no distributed code): measured at N=1 only"
     return {"images_per_sec": global_batch / (ms / 1e3), "ms_per_step": ms, "mode": mode, "eager_ms_per_step": eager_ms,
             "global_batch": global_batch, "per_rank_batch": hi - lo, "steps_timed": steps,
             "final_loss": float(losses[-1].item()), "afr_launches_per_step": int(launches),
-            "params": sum(p.numel() for p in net.parameters()),
+            "params": sum(p.numel() for p in net.parameters()), "timeline_ms": timeline,
+            "reference_eager_ms_per_step": ref_ms, "speedup_vs_reference_eager": (ref_ms / ms) if ref_ms else None,
+            "reference_note": ref_note,
             "note": "variant=3 c=3 32x32 fp32, AdamW lr 3e-4, H2D of the batch and one flat-gradient NCCL all-reduce per step"}
+
+
+def ddp_grad_check(afr, ws, rank, global_batch=64):
+    """NCCL + the afr kernels together: every rank runs forward/backward on ITS shard of one fixed global
+    batch (same images, timesteps and q-sample noise on every rank, sliced), the flat gradient goes through
+    the step's single all-reduce (mean), and rank 0 compares it with the gradient of the whole batch
+    computed alone.  fp32 without TF32; tolerance 1e-5 rel-max.  At N=1 the shards are two halves of the
+    batch run one after the other and averaged (same arithmetic, no collective)."""
+    from aliasfree_b200 import parallel
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        net = afr.UNet(c_in=3, c_out=3, image_size=32, f_settings=FS, variant=3).cuda().train()
+        diff = afr.Diffusion(noise_steps=1000, img_size=32, device="cuda")
+        ddp = parallel.FlatGradAllReduce(net)                  # broadcasts rank 0's parameters
+        g = torch.Generator().manual_seed(11)
+        images = (torch.rand(global_batch, 3, 32, 32, generator=g) * 2 - 1).cuda()
+        t = torch.randint(1, 1000, (global_batch,), generator=g).cuda()
+        noise = torch.randn(global_batch, 3, 32, 32, generator=g).cuda()
+
+        def grad_of(lo, hi):
+            ddp.zero_grad()
+            x_t, eps = diff.noise_images(images[lo:hi], t[lo:hi], noise=noise[lo:hi])
+            torch.nn.functional.mse_loss(net(x_t, t[lo:hi]), eps).backward()
+            return ddp.flat
+
+        l0 = afr.launch_count()
+        shards = ws if ws > 1 else 2
+        if ws > 1:
+            lo, hi = parallel.shard_bounds(global_batch, rank, ws)
+            grad_of(lo, hi)
+            ddp.sync()
+            reduced = ddp.flat.clone()
+        else:
+            reduced = torch.zeros_like(ddp.flat)
+            for r in range(shards):
+                reduced += grad_of(*parallel.shard_bounds(global_batch, r, shards)) / shards
+        whole = grad_of(0, global_batch).clone()
+        err = float((reduced - whole).abs().max() / whole.abs().max())
+        return {"ok": bool(err <= 1e-5), "rel_max_err": err, "tolerance": 1e-5, "shards": shards, "global_batch": global_batch,
+                "collective": "nccl all_reduce(sum)/N over the flat fp32 gradient" if ws > 1 else "none (N=1: two half-batches averaged)",
+                "grad_elements": int(whole.numel()), "afr_launches": int(afr.launch_count() - l0),
+                "note": "variant=3 fp32 (TF32 off); sharded mean gradient vs the whole-batch gradient"}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+
+
+# ---- configs[0]: variant 1 (Config B), MNIST-shaped 1x32x32, batch 16, 50-step schedule ------------------
+def config0(afr, with_cpu):
+    """The reference's own CPU-runnable case (Train.ipynb:48-64 parameters, noise_steps=50 => 49 reverse
+    steps) on the GPU: our package eager and graph-replayed, the unmodified reference eager on the same GPU,
+    and (rank 0, N=1) the unmodified reference on the host cores."""
+    torch.manual_seed(42)
+    net = afr.UNet(c_in=1, c_out=1, image_size=32, f_settings=FS, variant=1).cuda().eval()
+    diff = afr.Diffusion(noise_steps=50, img_size=32, device="cuda")
+    out = {"workload": "UNet variant=1, 1x32x32, n=16, noise_steps=50 (49 reverse steps) -> images/sec"}
+
+    def wall(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            t = time.perf_counter(); fn(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t)
+        return float(np.median(ts))
+
+    l0 = afr.launch_count()
+    s = wall(lambda: diff.sample(net, 16, 1))
+    out["ours_eager_s"] = s
+    out["afr_launches_per_sample_call"] = int((afr.launch_count() - l0) // 4)
+    s_g = wall(lambda: diff.sample(net, 16, 1, cuda_graph=True))
+    out["ours_cuda_graph_s"] = s_g
+    out["images_per_sec"] = 16 / min(s, s_g)
+    ref = load_reference()
+    if ref is not None:
+        import logging
+        logging.disable(logging.INFO)
+        rm = ref[2]
+        try:
+            rnet = rm.UNet(c_in=1, c_out=1, image_size=32, device="cuda", f_settings=FS, variant=1).cuda()
+            rnet.load_state_dict(net.state_dict(), strict=True)
+            rdiff = rm.Diffusion(noise_steps=50, img_size=32, device="cuda")
+            r = wall(lambda: rdiff.sample(rnet, n=16, image_channels=1))
+            out["reference_eager_gpu_s"] = r
+            out["speedup_vs_reference_eager_gpu"] = r / min(s, s_g)
+            if with_cpu:
+                torch.set_num_threads(len(os.sched_getaffinity(0)))
+                cnet = rm.UNet(c_in=1, c_out=1, image_size=32, device="cpu", f_settings=FS, variant=1)
+                cdiff = rm.Diffusion(noise_steps=50, img_size=32, device="cpu")
+                cdiff.sample(cnet, n=2, image_channels=1)
+                t = time.perf_counter(); cdiff.sample(cnet, n=16, image_channels=1)
+                out["reference_cpu_s"] = time.perf_counter() - t
+                out["reference_cpu_threads"] = torch.get_num_threads()
+                out["speedup_vs_reference_cpu"] = out["reference_cpu_s"] / min(s, s_g)
+        except Exception as e:
+            out["reference_error"] = repr(e)[:200]
+    else:
+        out["reference_note"] = "no reference install (baseline/_ref) on this machine"
+    return out
 
 
 # ---- Config-E rotation sweep (BASELINE configs[3]) -----------------------------------------------------
@@ -452,10 +691,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ddpm-batch", type=int, default=4096)
     ap.add_argument("--train-batch", type=int, default=256)
+    ap.add_argument("--ddpm-schedule", type=int, default=1000, help="noise_steps of the configs[2] run (1000 = the full 999-step sampler)")
+    ap.add_argument("--quick", action="store_true", help="development runs: 50-step schedule, 5 training steps, no sustained / config[0] legs")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--path", default="auto", choices=["auto", "direct", "tma", "generic", "direct_general", "tma_general"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.quick:
+        args.ddpm_schedule = min(args.ddpm_schedule, 51)
 
     if args.impl == "reference":
         return run_reference(args)
@@ -484,7 +727,7 @@ def main():
         step()
     clocks.start()
     total_ms, per = timed_loop(step, args.steps, 0, ws, per_step_events=True)
-    launches = afr.launch_count() - l0 - args.warmup
+    launches = afr.launch_count() - l0 - args.warmup          # launches inside the timed region (= steps)
     kernel = afr.last_kernel()
     ms_step = total_ms / args.steps
     value = ws * nbytes / ms_step / 1e6
@@ -500,6 +743,16 @@ def main():
     roof = {"bound": "hbm", "kernel": kernel, "achieved": nbytes / k_ms / 1e6, "peak": peak, "unit": "GB/s",
             "frac": nbytes / k_ms / 1e6 / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": k_ms}
+    if not args.quick:
+        # the timed region above is a burst of a few ms; the same launch repeated back to back for >= 1 s is
+        # power-limited on this part (sw_power_cap), so both figures are reported
+        sus_clk = ClockSampler(local)
+        n_sus = int(max(200, 1500.0 / max(ms_step, 1e-3)))
+        sus_clk.start()
+        sus_ms, _ = timed_loop(step, n_sus, 0, ws)
+        sus = sus_clk.stop()
+        roof["sustained"] = {"achieved": nbytes / (sus_ms / n_sus) / 1e6, "frac": nbytes / (sus_ms / n_sus) / 1e6 / peak,
+                             "launches": n_sus, "seconds": sus_ms / 1e3, "sm_mhz": sus.get("sm_mhz"), "reasons": sus.get("reasons")}
 
     # end to end with HOST buffers: every step moves x host->device and y device->host through the
     # package's host-tensor API (HostPipeline: chunked H2D | kernel | D2H on three streams, so PCIe
@@ -526,7 +779,11 @@ def main():
            "api": "aliasfree_b200.HostPipeline.filtered_gelu: pinned host x -> 32 chunks (H2D | afr_filtered_gelu_fwd | D2H "
                   "overlapped on three streams) -> pinned host y",
            "kernel_launches_per_step": int(e2e_launches),
-           "sequential_value": ws * nbytes / (seq_total / e_steps) / 1e6, "sequential_ms_per_step": seq_total / e_steps}
+           "sequential_value": ws * nbytes / (seq_total / e_steps) / 1e6, "sequential_ms_per_step": seq_total / e_steps,
+           "per_gpu_value": nbytes / (e_total / e_steps) / 1e6,
+           "note": "PCIe-bound: H2D and D2H of 512 MiB each per step and GPU; with N > 1 all ranks' pinned buffers sit in one "
+                   "host memory / PCIe complex (every GPU reports NUMA node 0), so the aggregate does not scale with N -- a "
+                   "host-side limit, not a kernel or NCCL one"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -552,23 +809,35 @@ def main():
             out["sweep"] = sweep(afr, quick=not args.full_sweep, grid=args.grid_sweep)
         except Exception as e:                      # never lose the headline to a side table
             out["sweep"] = {"error": repr(e)[:300]}
+    side_steps = 5 if args.quick else max(args.steps, 20)
     if not args.no_ddpm:
         torch.cuda.empty_cache()
         try:
-            out["ddpm_v3"] = ddpm_v3(afr, ws, rank, args.ddpm_batch, steps=min(args.steps, 5), warmup=3)
+            out["ddpm_v3"] = ddpm_v3(afr, ws, rank, args.ddpm_batch, steps=min(args.steps, 5), warmup=3,
+                                     schedule=args.ddpm_schedule)
         except Exception as e:
             out["ddpm_v3"] = {"error": repr(e)[:300]}
     if not args.no_train:
         torch.cuda.empty_cache()
         try:
-            out["train_v3"] = train_v3(afr, ws, rank, args.train_batch, steps=min(args.steps, 5), warmup=3)
+            out["train_v3"] = train_v3(afr, ws, rank, args.train_batch, steps=side_steps, warmup=3)
         except Exception as e:
             out["train_v3"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+        try:
+            out["ddp_grad_check"] = ddp_grad_check(afr, ws, rank)
+        except Exception as e:
+            out["ddp_grad_check"] = {"ok": False, "error": repr(e)[:300]}
     if not args.no_ddpm and ws == 1:
         try:
             out["config_e"] = config_e(afr)
         except Exception as e:
             out["config_e"] = {"error": repr(e)[:300]}
+        if not args.quick:
+            try:
+                out["config0"] = config0(afr, with_cpu=not args.no_cpu)
+            except Exception as e:
+                out["config0"] = {"error": repr(e)[:300]}
     if rank == 0:
         emit(out)
     if ws > 1:

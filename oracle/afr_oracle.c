@@ -383,3 +383,17 @@ int afr_oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* Thread count of the OpenMP regions above.  torchrun exports OMP_NUM_THREADS=1 and libgomp reads the
+ * environment once, when it is first loaded (by `import torch`, long before bench.py's CPU arm runs),
+ * so the arm sets the count explicitly.  Returns the count now in force. */
+int afr_oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}

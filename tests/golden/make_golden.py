@@ -14,6 +14,7 @@ Outputs (all small .npz files next to this script):
   blocks.npz    DoubleConv_F, Down_F/FF/FFF, Up_F/FF/FFF forward + input grads
   unet.npz      UNet variants 1/2/3 forward (+ variant 3 input grad)
   sampler.npz   Diffusion.sample short schedules (with and without theta), per-step states
+  train.npz     the reference's own train() (modules/ddpm_utils.py:483-519), one epoch of three batches
 """
 import os
 import sys
@@ -192,6 +193,58 @@ def gen_sampler(models):
     np.savez_compressed(os.path.join(HERE, "sampler.npz"), **out)
 
 
+class _TensorSample:
+    """Mixin for the Diffusion handed to the reference's train(): ``sample`` returns the image tensor
+    only.  Upstream ``sample`` returns a tuple which train() passes to torchvision's make_grid -- a
+    TypeError at the end of epoch 0; the train() code itself runs unmodified."""
+
+    def sample(self, *a, **kw):
+        return super().sample(*a, **kw)[0]
+
+
+TRAIN_CFG = dict(steps=3, batch=4, size=16, noise_steps=40, lr=3e-4, seed=77, image_gen_n=2)
+
+
+def train_batches():
+    c = TRAIN_CFG
+    return [(torch.from_numpy(seeded_array(f"train_images_{i}", (c["batch"], 3, c["size"], c["size"]))).clamp(-1, 1),
+             torch.zeros(c["batch"], dtype=torch.long)) for i in range(c["steps"])]
+
+
+def gen_train(utils, models):
+    """Run the reference's train() on CPU: timesteps, q-sample noise and the end-of-epoch sampling all
+    draw from torch's default CPU generator (seeded), which the GPU test replays."""
+    import tempfile
+    c = TRAIN_CFG
+    net = models.UNet(c_in=3, c_out=3, image_size=c["size"], device="cpu", f_settings=F_SETTINGS, variant=3)
+    fill_params_(net)
+    Diff = type("Diffusion", (_TensorSample, models.Diffusion), {})
+    diff = Diff(noise_steps=c["noise_steps"], img_size=c["size"], device="cpu")
+    args = utils.argument(run_name="golden_train", epochs=1, batch_size=c["batch"], image_size=c["size"],
+                          image_channels=3, device="cpu", lr=c["lr"], noise_steps=c["noise_steps"],
+                          image_gen_n=c["image_gen_n"])
+    preds = []
+    hook = net.register_forward_hook(lambda m, a, o: preds.append(o.detach().clone()) if m.training else None)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            torch.manual_seed(c["seed"])
+            losses = utils.train(args, os.path.join(tmp, "ckpt.pt"), train_batches(), net, diff)
+            saved = sorted(os.listdir(os.path.join(tmp, "results", "golden_train")))
+        finally:
+            os.chdir(cwd)
+    hook.remove()
+    out = {"preds": torch.stack(preds).numpy(), "saved": np.array(len(saved))}
+    if losses is not None:
+        out["loss_all"] = np.asarray(losses, np.float64)
+    sd = net.state_dict()
+    for key in ("inc.conv1.weight", "down2.conv.1.norm2.weight", "bot2.norm2.bias", "up1.emb_layer.1.bias",
+                "sa3.mha.in_proj_weight", "outc.weight"):
+        out["param." + key] = sd[key].numpy()
+    np.savez_compressed(os.path.join(HERE, "train.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     torch.use_deterministic_algorithms(False)
@@ -202,6 +255,7 @@ def main():
     gen_blocks(utils)
     gen_unet(models)
     gen_sampler(models)
+    gen_train(utils, models)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -304,6 +304,80 @@ def test_full_size_properties(afr, oracle):
         assert relmax(host(outs["tma"][1][b, c]), oracle.filtered_gelu_bwd(xs, dys, kn, kn)) <= FP32_TOL
 
 
+HEADLINE_SHAPES = [(256, 128, 64, 64), (64, 64, 128, 128), (16, 64, 256, 256), (128, 512, 32, 32)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("shape", HEADLINE_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_headline_tensors_sampled_against_oracle(afr, oracle, shape, dtype):
+    """The BASELINE configs[4] tensors themselves (the [256,128,64,64] bench tensor, the 128^2 and 256^2
+    grid points with B > 1, the 512-channel point): forward and adjoint of the fused op plus both
+    standalone resamplers, run on the WHOLE tensor; 32 planes drawn over the full (b, c) range are
+    compared with the oracle (planes are independent, so the oracle only has to compute those)."""
+    B, C, H, W = shape
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
+    kn = k.numpy()
+    gen = torch.Generator(device="cuda").manual_seed(B + H)
+    x = torch.randn(shape, device="cuda", generator=gen).to(dtype)
+    dy = torch.randn(shape, device="cuda", generator=gen).to(dtype)
+    kt = afr.Taps(k)
+    y = afr.ops._fgelu_fwd(x, None, kt, kt)
+    kern_f = afr.last_kernel()
+    dx = afr.ops._fgelu_bwd(x, None, dy, kt, kt)
+    d = afr.ops._down_fwd(x, kt)
+    torch.cuda.synchronize()
+    assert kern_f == "fgelu3_tma_kernel<sym>"
+    rng = np.random.default_rng(B * 7 + H)
+    planes = sorted({0, B * C - 1, *rng.integers(0, B * C, 30).tolist()})
+    idx = torch.tensor(planes, device="cuda")
+    pick = lambda t: host(t.reshape(B * C, *t.shape[2:])[idx])
+    xs, dys = pick(x), pick(dy)
+    assert relmax(pick(y), oracle.filtered_gelu(xs, kn, kn)) <= tol
+    assert relmax(pick(dx), oracle.filtered_gelu_bwd(xs, dys, kn, kn)) <= tol
+    assert relmax(pick(d), oracle.down2x(xs, kn)) <= tol
+    del y, dx, d
+    u = afr.ops._up_fwd(x[: max(1, B // 4)], kt, dtype)          # a quarter of the batch: the output is 4x the input
+    sub = [p for p in planes if p < max(1, B // 4) * C]
+    uidx = torch.tensor(sub, device="cuda")
+    got = host(u.reshape(-1, 2 * H, 2 * W)[uidx])
+    assert relmax(got, oracle.up2x(host(x.reshape(B * C, H, W)[uidx]), kn)) <= tol
+
+
+@pytest.mark.parametrize("path", ["tma", "tma_general", "direct", "direct_general"])
+@pytest.mark.parametrize("shape", [(2, 4, 32, 32), (1, 2, 64, 64), (2, 2, 16, 24), (1, 3, 24, 136), (1, 2, 40, 264),
+                                   (3, 2, 8, 8), (5, 3, 4, 4)])
+def test_oracle_bf16_every_n3_family_fwd_and_adjoint(afr, oracle, shape, path):
+    """bf16 storage through each N == 3 kernel family explicitly (TMA ring with symmetric and with general
+    taps, direct / whole-plane kernels), forward, adjoint and the fused residual, against the fp32 oracle
+    evaluated on the bf16-rounded inputs."""
+    if path.startswith("tma") and (shape[-1] < 8 or shape[-2] < 2):
+        pytest.skip("TMA cannot describe 4-wide bf16 rows (8 bytes)")
+    rng = np.random.default_rng(sum(shape))
+    k = oracle.lowpass_taps(np.pi / 2, 3, 2.0)
+    xb = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
+    rb = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
+    dyb = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
+    x32, r32, dy32 = host(xb), host(rb), host(dyb)
+    want_kernel = {"tma": "fgelu3_tma_kernel<sym>", "tma_general": "fgelu3_tma_kernel",
+                   "direct": "fgelu3_direct_kernel<sym>", "direct_general": "fgelu3_direct_kernel"}[path]
+    afr.set_path(path)
+    try:
+        kt = afr.Taps(k)
+        y = afr.ops._fgelu_fwd(xb, None, kt, kt)
+        assert afr.last_kernel() == want_kernel and y.dtype == torch.bfloat16
+        assert relmax(host(y), oracle.filtered_gelu(x32, k, k)) <= BF16_TOL
+        dx = afr.ops._fgelu_bwd(xb, None, dyb, kt, kt)
+        assert afr.last_kernel() == want_kernel and dx.dtype == torch.bfloat16
+        assert relmax(host(dx), oracle.filtered_gelu_bwd(x32, dy32, k, k)) <= BF16_TOL
+        yr = afr.ops._fgelu_fwd(xb, rb, kt, kt)
+        assert relmax(host(yr), oracle.filtered_gelu(x32 + r32, k, k)) <= BF16_TOL
+        dxr = afr.ops._fgelu_bwd(xb, rb, dyb, kt, kt)
+        assert relmax(host(dxr), oracle.filtered_gelu_bwd(x32 + r32, dy32, k, k)) <= BF16_TOL
+    finally:
+        afr.set_path("auto")
+
+
 def test_kernel_selection(afr):
     k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
     afr.filtered_gelu(torch.randn(2, 2, 32, 32, device="cuda"), k, k)

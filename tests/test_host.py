@@ -16,6 +16,14 @@ from conftest import ROOT, golden
 FS = dict(kernel_size=3, kaiser_beta=2, omega_c_down=np.pi / 2, omega_c_up=np.pi / 2)
 
 
+def _reference():
+    """The unmodified reference: /root/reference here, baseline/_ref elsewhere (tools/install_ref.py)."""
+    from baseline import ref_loader
+    if not ref_loader.available():
+        pytest.skip("no reference checkout on this machine")
+    return ref_loader.load()
+
+
 @pytest.fixture(scope="module")
 def afr():
     import aliasfree_b200 as m
@@ -100,14 +108,7 @@ def test_state_dict_keys_match_reference_layout(afr):
 
 
 def test_state_dict_is_strictly_loadable_from_reference():
-    if not os.path.isdir("/root/reference/modules"):
-        pytest.skip("no reference checkout on this machine")
-    import types
-    for name in ("matplotlib", "matplotlib.pyplot", "imageio"):
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    sys.path.insert(0, "/root/reference")
-    import modules.ddpm_models as rm
+    rm = _reference()[2]
     import aliasfree_b200 as afr
     for v in (0, 1, 2, 3, 4):
         ref = rm.UNet(c_in=3, c_out=3, image_size=16, device="cpu", f_settings=FS, variant=v)
@@ -119,15 +120,7 @@ def test_state_dict_is_strictly_loadable_from_reference():
 def test_patch_rebinds_reference_names_and_restores():
     """patch() makes the reference's own UNet build from our block classes (checked on CPU by
     construction + strict state_dict exchange; the forward needs a GPU) and unpatch() undoes it."""
-    if not os.path.isdir("/root/reference/modules"):
-        pytest.skip("no reference checkout on this machine")
-    import types
-    for name in ("matplotlib", "matplotlib.pyplot", "imageio"):
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    sys.path.insert(0, "/root/reference")
-    import modules.ddpm_models as rm
-    import modules.ddpm_utils as ru
+    ru, rm = _reference()[1:]
     import aliasfree_b200 as afr
     orig = (rm.DoubleConv_F, ru.custom_upsample, rm.Diffusion.__dict__["rotate_2d_matrix"])
     ref_sd = rm.UNet(c_in=3, c_out=3, image_size=16, device="cpu", f_settings=FS, variant=3).state_dict()
@@ -150,10 +143,7 @@ def test_patch_rebinds_reference_names_and_restores():
 
 def test_variant0_unet_runs_on_cpu_and_matches_reference():
     """Variant 0 has no filters, so the wiring itself can be checked on CPU against the reference."""
-    if not os.path.isdir("/root/reference/modules"):
-        pytest.skip("no reference checkout on this machine")
-    sys.path.insert(0, "/root/reference")
-    import modules.ddpm_models as rm
+    rm = _reference()[2]
     import aliasfree_b200 as afr
     from _fill import fill_params_
     ref = fill_params_(rm.UNet(c_in=3, c_out=3, image_size=16, device="cpu", variant=0))
@@ -247,3 +237,30 @@ def test_shift_matches_scipy_grid_wrap(afr):
         want = ndimage.shift(input=x.numpy(), shift=(0, 0, v, h), mode="grid-wrap")
         got = afr.Diffusion.shift_2d_matrix(x, h, v, "cpu").numpy()
         np.testing.assert_allclose(got, want, atol=2e-6)
+
+
+def test_blocks_deepcopy_and_pickle_after_taps_were_cached(afr):
+    """The reference's EMA pattern deep-copies the model and users torch.save whole models; a cached
+    ``Taps`` must not get in the way (it holds a tensor, the C pointer is taken at launch time)."""
+    import copy
+    import io
+    import pickle
+    blk = afr.DoubleConv_F(4, 4, residual=True, f_settings=FS)
+    up, dn = blk._filters()                                  # what the first forward caches
+    assert up.n == 3 and up.ptr.value == up.t.data_ptr()
+    clone = copy.deepcopy(blk)
+    up2, _ = clone._filters()
+    assert up2.t.data_ptr() != up.t.data_ptr() and torch.equal(up2.t, up.t)   # its own storage, same taps
+    back = pickle.loads(pickle.dumps(blk))
+    assert torch.equal(back._filters()[0].t, up.t)
+    buf = io.BytesIO()
+    net = afr.UNet(c_in=3, c_out=3, image_size=16, f_settings=FS, variant=3)
+    for m in net.modules():
+        if isinstance(m, afr.DoubleConv_F):
+            m._filters()
+    torch.save(net, buf)
+    buf.seek(0)
+    again = torch.load(buf, weights_only=False)
+    assert sorted(again.state_dict()) == sorted(net.state_dict())
+    t = afr.Taps(afr.circularLowpassKernel(np.pi / 2, 3, 2))
+    assert pickle.loads(pickle.dumps(t)).n == 3 and copy.deepcopy(t).t.data_ptr() != t.t.data_ptr()

@@ -1,5 +1,5 @@
 // Throughput microbenchmark of candidate GELU evaluations (compute only, values in registers).
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gelu_ubench gelu_ubench.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o gelu_ubench gelu_ubench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>

@@ -1,7 +1,7 @@
 // Issue / pipe interference microbenchmark for the fused-kernel instruction mix (sm_100a).
 // Each warp runs ITER iterations of an unrolled body made of independent packed-FMA chains
 // (FFMA2), scalar FMA-pipe ops, ALU ops (FMNMX) and MUFU.EX2, with W warps per SM sub-partition;
-// reports cycles per iteration per warp and per SMSP.   nvcc -arch=sm_100a -O3 -o pipe_ubench pipe_ubench.cu
+// reports cycles per iteration per warp and per SMSP.   nvcc -arch=sm_100a -O3 -cudart shared -o pipe_ubench pipe_ubench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 typedef unsigned long long u64;
