@@ -9,7 +9,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libafr_b200.so")
-SOURCES = ["afr_api.cu", "afr_generic.cu", "afr_n3.cu", "afr_stripn.cu", "afr_rotate.cu"]
+SOURCES = ["afr_api.cu", "afr_generic.cu", "afr_n3.cu", "afr_stripn.cu", "afr_rotate.cu", "afr_small.cu"]
 HEADERS = ["afr_common.cuh", "afr_kernels.h", os.path.join("..", "..", "include", "afr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "--threads", "0"]
@@ -64,6 +64,8 @@ def _declare(L):
     L.afr_launch_count.restype = ctypes.c_uint64
     L.afr_up2x_fwd.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci, ci, vp]
     L.afr_up2x_bwd.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci, ci, vp]
+    L.afr_up2x_fwd_strided.argtypes = [vp, vp, ci, ci, ci, ci, i64, vp, ci, ci, ci, vp]
+    L.afr_up2x_bwd_strided.argtypes = [vp, vp, ci, ci, ci, ci, i64, vp, ci, ci, vp]
     L.afr_down2x_fwd.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci, vp]
     L.afr_down2x_bwd.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci, vp]
     L.afr_filtered_gelu_fwd.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
@@ -73,7 +75,7 @@ def _declare(L):
     L.afr_rotate_periodic_cubic.argtypes = [vp, vp, ci, ci, ci, ci, cd, ci, vp]
     L.afr_ddpm_update.argtypes = [vp, vp, vp, i64, cf, cf, cf, vp]
     L.afr_ddpm_update_table.argtypes = [vp, vp, vp, i64, vp, vp, vp]
-    for n in ("afr_up2x_fwd", "afr_up2x_bwd", "afr_down2x_fwd", "afr_down2x_bwd",
+    for n in ("afr_up2x_fwd", "afr_up2x_bwd", "afr_down2x_fwd", "afr_down2x_bwd", "afr_up2x_fwd_strided", "afr_up2x_bwd_strided",
               "afr_filtered_gelu_fwd", "afr_filtered_gelu_bwd", "afr_filtered_gelu_affine_fwd", "afr_groupnorm1_affine",
               "afr_rotate_periodic_cubic", "afr_ddpm_update", "afr_ddpm_update_table"):
         getattr(L, n).restype = ci
@@ -81,7 +83,8 @@ def _declare(L):
 
 
 EXPORTS = ("afr_version", "afr_last_error", "afr_status_string", "afr_set_path", "afr_last_kernel",
-           "afr_launch_count", "afr_up2x_fwd", "afr_up2x_bwd", "afr_down2x_fwd", "afr_down2x_bwd",
+           "afr_launch_count", "afr_up2x_fwd", "afr_up2x_bwd", "afr_up2x_fwd_strided", "afr_up2x_bwd_strided",
+           "afr_down2x_fwd", "afr_down2x_bwd",
            "afr_filtered_gelu_fwd", "afr_filtered_gelu_bwd", "afr_filtered_gelu_affine_fwd", "afr_groupnorm1_affine",
            "afr_rotate_periodic_cubic", "afr_ddpm_update", "afr_ddpm_update_table")
 
@@ -105,6 +108,12 @@ def lib():
 
 
 PATHS = {"auto": 0, "direct": 1, "tma": 2, "generic": 3, "direct_general": 4, "tma_general": 5}
+
+
+def PATHS_AUTO():
+    """True while the kernel-family selection is AUTO (the strided resamplers exist only there).
+    An out-of-range argument makes afr_set_path a pure query."""
+    return lib().afr_set_path(-1) == PATHS["auto"]
 
 
 def set_path(name):

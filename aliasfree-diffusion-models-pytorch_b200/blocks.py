@@ -216,8 +216,8 @@ class _FilteredUp(_TimeConditioned):
         self._make_emb(emb_dim, out_channels)
 
     def forward(self, x, skip_x, t):
-        up = ops.up2x(x, self.sinc_filter, out_dtype=skip_x.dtype)
-        return self._add_emb(self.conv(torch.cat([skip_x, up], dim=1)), t)
+        # the upsampler writes straight into its half of the concatenated buffer
+        return self._add_emb(self.conv(ops.up2x_cat(skip_x, x, self.sinc_filter)), t)
 
 
 class Down_FF(_FilteredDown):

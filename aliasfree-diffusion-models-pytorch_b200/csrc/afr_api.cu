@@ -152,6 +152,12 @@ int afr_up2x_fwd(const void *x, void *u, int B, int C, int H, int W, const float
     cudaStream_t s = (cudaStream_t)stream;
     begin_call();
     const int path = current_path();
+    const bool small_up = N == 3 && path == AFR_PATH_AUTO && small_up_supported(H, W, x, u, 4L * H * W, out_dtype);
+    if (small_up && (warp_up_shape(H, W) || !n3_up_supported(H, W, x, u, in_dtype, out_dtype))) {
+        Taps3 k; set_taps3(k, taps, false);
+        g_last_kernel = warp_up_shape(H, W) ? "up3_warp_kernel" : "up3_group_kernel";
+        return cuda_status(small_up_like(x, u, planes, 1, 4L * H * W, H, W, k, in_dtype, out_dtype, s), g_last_kernel);
+    }
     if (N == 3 && path != AFR_PATH_GENERIC && n3_up_supported(H, W, x, u, in_dtype, out_dtype)) {
         Taps3 k; set_taps3(k, taps, false);
         g_last_kernel = "up3_kernel";
@@ -181,6 +187,12 @@ int afr_up2x_bwd(const void *du, void *dx, int B, int C, int H, int W, const flo
     const int path = current_path();
     if (du_dtype != dx_dtype)
         return fail(AFR_ERR_UNSUPPORTED, "up2x_bwd needs du and dx of one dtype (cast du on the host side)");
+    const bool small_dn = N == 3 && path == AFR_PATH_AUTO && small_down_supported(2 * H, 2 * W, du, dx, 4L * H * W, du_dtype);
+    if (small_dn && (warp_down_shape(2 * H, 2 * W) || !n3_down_supported(2 * H, 2 * W, du, dx, du_dtype))) {
+        Taps3 k; set_taps3(k, taps, true);
+        g_last_kernel = warp_down_shape(2 * H, 2 * W) ? "down3_warp_kernel" : "down3_group_kernel";
+        return cuda_status(small_down_like(du, dx, planes, 1, 4L * H * W, 2 * H, 2 * W, k, du_dtype, s), g_last_kernel);
+    }
     if (N == 3 && path != AFR_PATH_GENERIC && n3_down_supported(2 * H, 2 * W, du, dx, du_dtype)) {
         Taps3 k; set_taps3(k, taps, true);
         g_last_kernel = "down3_kernel";
@@ -196,6 +208,58 @@ int afr_up2x_bwd(const void *du, void *dx, int B, int C, int H, int W, const flo
                        "down_like_generic_kernel");
 }
 
+int afr_up2x_fwd_strided(const void *x, void *u, int B, int C, int H, int W, int64_t out_batch_stride,
+                         const float *taps, int N, int in_dtype, int out_dtype, void *stream)
+{
+    if (int rc = check_common(B, C, H, W, taps, N)) return rc;
+    if (!dtype_ok(in_dtype) || !dtype_ok(out_dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if (out_batch_stride < 4L * C * H * W) return fail(AFR_ERR_BAD_SHAPE, "out_batch_stride smaller than C*2H*2W");
+    const long planes = (long)B * C;
+    if (planes == 0) return AFR_OK;
+    if (!x || !u) return fail(AFR_ERR_NULL_POINTER, "x or u is NULL");
+    begin_call();
+    if (N != 3 || current_path() != AFR_PATH_AUTO)
+        return fail(AFR_ERR_UNSUPPORTED, "strided up2x needs N == 3 and the AUTO kernel path");
+    Taps3 k; set_taps3(k, taps, false);
+    const bool strip_ok = n3_up_supported(H, W, x, u, in_dtype, out_dtype) && (out_batch_stride % 8) == 0;
+    if (small_up_supported(H, W, x, u, (long)out_batch_stride, out_dtype) && (warp_up_shape(H, W) || !strip_ok)) {
+        g_last_kernel = warp_up_shape(H, W) ? "up3_warp_kernel" : "up3_group_kernel";
+        return cuda_status(small_up_like(x, u, planes, C, (long)out_batch_stride, H, W, k, in_dtype, out_dtype,
+                                         (cudaStream_t)stream), g_last_kernel);
+    }
+    if (!strip_ok)
+        return fail(AFR_ERR_UNSUPPORTED, "strided up2x needs W %% 4 == 0, 32-byte aligned slice base and batch stride (H=%d W=%d)", H, W);
+    g_last_kernel = "up3_kernel";
+    return cuda_status(n3_up_like(x, u, planes, H, W, k, in_dtype, out_dtype, (cudaStream_t)stream, C, (long)out_batch_stride),
+                       "up3_kernel");
+}
+
+int afr_up2x_bwd_strided(const void *du, void *dx, int B, int C, int H, int W, int64_t du_batch_stride,
+                         const float *taps, int N, int dtype, void *stream)
+{
+    if (int rc = check_common(B, C, H, W, taps, N)) return rc;
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if (du_batch_stride < 4L * C * H * W) return fail(AFR_ERR_BAD_SHAPE, "du_batch_stride smaller than C*2H*2W");
+    const long planes = (long)B * C;
+    if (planes == 0) return AFR_OK;
+    if (!du || !dx) return fail(AFR_ERR_NULL_POINTER, "du or dx is NULL");
+    begin_call();
+    if (N != 3 || current_path() != AFR_PATH_AUTO)
+        return fail(AFR_ERR_UNSUPPORTED, "strided up2x adjoint needs N == 3 and the AUTO kernel path");
+    Taps3 k; set_taps3(k, taps, true);
+    const bool strip_ok = n3_down_supported(2 * H, 2 * W, du, dx, dtype) && (du_batch_stride % 8) == 0;
+    if (small_down_supported(2 * H, 2 * W, du, dx, (long)du_batch_stride, dtype) && (warp_down_shape(2 * H, 2 * W) || !strip_ok)) {
+        g_last_kernel = warp_down_shape(2 * H, 2 * W) ? "down3_warp_kernel" : "down3_group_kernel";
+        return cuda_status(small_down_like(du, dx, planes, C, (long)du_batch_stride, 2 * H, 2 * W, k, dtype,
+                                           (cudaStream_t)stream), g_last_kernel);
+    }
+    if (!strip_ok)
+        return fail(AFR_ERR_UNSUPPORTED, "strided up2x adjoint needs W %% 4 == 0 and 16-byte aligned slice base / batch stride (H=%d W=%d)", H, W);
+    g_last_kernel = "down3_kernel";
+    return cuda_status(n3_down_like(du, dx, planes, 2 * H, 2 * W, k, dtype, (cudaStream_t)stream, C, (long)du_batch_stride),
+                       "down3_kernel");
+}
+
 int afr_down2x_fwd(const void *v, void *y, int B, int C, int H, int W, const float *taps, int N,
                    int dtype, void *stream)
 {
@@ -208,6 +272,12 @@ int afr_down2x_fwd(const void *v, void *y, int B, int C, int H, int W, const flo
     cudaStream_t s = (cudaStream_t)stream;
     begin_call();
     const int path = current_path();
+    const bool small_dn = N == 3 && path == AFR_PATH_AUTO && small_down_supported(H, W, v, y, (long)H * W, dtype);
+    if (small_dn && (warp_down_shape(H, W) || !n3_down_supported(H, W, v, y, dtype))) {
+        Taps3 k; set_taps3(k, taps, false);
+        g_last_kernel = warp_down_shape(H, W) ? "down3_warp_kernel" : "down3_group_kernel";
+        return cuda_status(small_down_like(v, y, planes, 1, (long)H * W, H, W, k, dtype, s), g_last_kernel);
+    }
     if (N == 3 && path != AFR_PATH_GENERIC && n3_down_supported(H, W, v, y, dtype)) {
         Taps3 k; set_taps3(k, taps, false);
         g_last_kernel = "down3_kernel";
@@ -236,6 +306,13 @@ int afr_down2x_bwd(const void *dy, void *dv, int B, int C, int H, int W, const f
     begin_call();
     const int path = current_path();
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    const bool small_up = N == 3 && path == AFR_PATH_AUTO && (H % 2) == 0 && (W % 2) == 0 &&
+                          small_up_supported(Ho, Wo, dy, dv, (long)H * W, dtype);
+    if (small_up && (warp_up_shape(Ho, Wo) || !n3_up_supported(Ho, Wo, dy, dv, dtype, dtype))) {
+        Taps3 k; set_taps3(k, taps, true);
+        g_last_kernel = warp_up_shape(Ho, Wo) ? "up3_warp_kernel" : "up3_group_kernel";
+        return cuda_status(small_up_like(dy, dv, planes, 1, (long)H * W, Ho, Wo, k, dtype, dtype, s), g_last_kernel);
+    }
     if (N == 3 && path != AFR_PATH_GENERIC && (H % 2) == 0 && (W % 2) == 0 &&
         n3_up_supported(Ho, Wo, dy, dv, dtype, dtype)) {
         Taps3 k; set_taps3(k, taps, true);

@@ -24,6 +24,13 @@ struct Taps3 {
     float k[3][3];
 };
 
+// Offset of plane p = (b, c) of a channel slice that lives inside a larger NCHW tensor: batch stride
+// `bstride`, dense channels of `plane` elements each.  C == 0 means a dense [planes, plane] tensor.
+__device__ __forceinline__ long strided_base(unsigned p, int C, long bstride, long plane)
+{
+    return C > 0 ? (long)(p / (unsigned)C) * bstride + (long)(p % (unsigned)C) * plane : (long)p * plane;
+}
+
 // ---- scalar / vector loads and stores with fp32 conversion --------------------
 __device__ __forceinline__ float ld1(const float *p) { return __ldg(p); }
 __device__ __forceinline__ float ld1(const bf16 *p)
@@ -196,6 +203,43 @@ __device__ __forceinline__ void gelu_erf_x2(float &a, float &b)
     unpack2(fma2(sv, pack2(ex2_approx(pa), ex2_approx(pb)), pack2(relu_nan(a), relu_nan(b))), a, b);
 }
 
+// ---- bf16-grade variants (kernels whose tensors are bf16) ---------------------------------------
+// The fused kernels are issue-bound, and bf16 storage halves the bytes but not the instructions, so the
+// bf16 kernels trade the ~1e-6 accuracy of the forms above (which bf16 rounding, 2^-9, cannot show) for
+// fewer packed FMAs: a degree-4 P (tools/fit_gelu_log.py 4 4.5; its leading coefficient is positive, so
+// t is clamped to 4.5, where t*Phi(-t) = 1.5e-5): max abs error 1.4e-4 and relative error <= 9.1e-4
+// (2^-10.1) for |x| < 1 -- both well inside the 2^-8 bound together with the output rounding -- and a
+// degree-4 S~ for the derivative (max abs error 2.5e-4 = 2^-12, clamp 4.5).
+#define AFR_LOW_T 4.5f
+#define AFR_Q4 2.371110529e-03f
+#define AFR_Q3 -3.545632926e-02f
+#define AFR_Q2 -4.825676429e-01f
+#define AFR_Q1 -1.141123898e+00f
+
+__device__ __forceinline__ float gelu_erf_low(float x)
+{
+    const float t = fminf(fabsf(x), AFR_LOW_T);
+    float p = AFR_Q4;
+    p = fmaf(p, t, AFR_Q3);
+    p = fmaf(p, t, AFR_Q2);
+    p = fmaf(p, t, AFR_Q1);
+    p = fmaf(p, t, AFR_P0);
+    return fmaf(-t, ex2_approx(p), relu_nan(x));
+}
+
+__device__ __forceinline__ void gelu_erf_low_x2(float &a, float &b)
+{
+    const f32x2 sv = pack2(fmaxf(-fabsf(a), -AFR_LOW_T), fmaxf(-fabsf(b), -AFR_LOW_T));
+    f32x2 p = splat2(AFR_Q4);
+    p = fma2(p, sv, splat2(-AFR_Q3));
+    p = fma2(p, sv, splat2(AFR_Q2));
+    p = fma2(p, sv, splat2(-AFR_Q1));
+    p = fma2(p, sv, splat2(AFR_P0));
+    float pa, pb;
+    unpack2(p, pa, pb);
+    unpack2(fma2(sv, pack2(ex2_approx(pa), ex2_approx(pb)), pack2(relu_nan(a), relu_nan(b))), a, b);
+}
+
 #define AFR_GELU_T 5.5f
 #define AFR_S8 3.792973455e-05f
 #define AFR_S7 -6.157795600e-04f
@@ -281,6 +325,44 @@ __device__ __forceinline__ void gelu_grad_scaled_mul_x2(float wa, float wb, floa
     unpack2(fma2(e, s, splat2(0.5f)), ha, hb);                          // 1/2 - m   (s = -S~)
     const f32x2 r = add2(pack2(copysign_bits(ha, wa), copysign_bits(hb, wb)), splat2(0.5f));
     unpack2(mul2(pack2(ga, gb), r), ga, gb);
+}
+
+// bf16-grade derivative: degree-4 S~ (tools/fit_gelu.py re-run with weight E, degree 4, T = 4.5)
+#define AFR_VT_LOW 3.8219481f          /* kappa * 4.5 */
+#define AFR_X4 -1.884529142e-02f
+#define AFR_X3 1.151408768e-01f
+#define AFR_X2 -2.969387650e-01f
+#define AFR_X1 9.305840670e-01f
+#define AFR_X0 -4.997464587e-01f
+
+__device__ __forceinline__ void gelu_grad_scaled_mul_low_x2(float wa, float wb, float &ga, float &gb)
+{
+    const float va = fminf(fabsf(wa), AFR_VT_LOW), vb = fminf(fabsf(wb), AFR_VT_LOW);
+    const f32x2 v = pack2(va, vb);
+    float qa, qb;
+    unpack2(mul2(v, v), qa, qb);
+    const f32x2 e = pack2(ex2_approx(-qa), ex2_approx(-qb));
+    f32x2 s = splat2(AFR_X4);
+    s = fma2(s, v, splat2(AFR_X3));
+    s = fma2(s, v, splat2(AFR_X2));
+    s = fma2(s, v, splat2(AFR_X1));
+    s = fma2(s, v, splat2(AFR_X0));
+    float ha, hb;
+    unpack2(fma2(e, s, splat2(0.5f)), ha, hb);
+    const f32x2 r = add2(pack2(copysign_bits(ha, wa), copysign_bits(hb, wb)), splat2(0.5f));
+    unpack2(mul2(pack2(ga, gb), r), ga, gb);
+}
+
+__device__ __forceinline__ float gelu_grad_scaled_low(float w)
+{
+    const float v = fminf(fabsf(w), AFR_VT_LOW);
+    const float e = ex2_approx(-v * v);
+    float s = AFR_X4;
+    s = fmaf(s, v, AFR_X3);
+    s = fmaf(s, v, AFR_X2);
+    s = fmaf(s, v, AFR_X1);
+    s = fmaf(s, v, AFR_X0);
+    return 0.5f + copysign_bits(fmaf(e, s, 0.5f), w);
 }
 
 __device__ __forceinline__ float gelu_grad_scaled(float w)

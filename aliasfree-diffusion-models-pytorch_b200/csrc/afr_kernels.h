@@ -60,12 +60,27 @@ cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, const float
                      bool bwd, int dtype, bool use_tma, bool allow_sym, cudaStream_t s, const char **kernel_name);
 // up-like with N==3: in [planes,H,W] -> out [planes,2H,2W]
 bool n3_up_supported(int H, int W, const void *in, const void *out, int in_dtype, int out_dtype);
+// (C > 0: the OUTPUT is a channel slice with batch stride out_bstride elements; C == 0: dense)
 cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,
-                       int in_dtype, int out_dtype, cudaStream_t s);
+                       int in_dtype, int out_dtype, cudaStream_t s, int C = 0, long out_bstride = 0);
 // down-like with N==3: in [planes,H,W] (H, W even, W % 8 == 0) -> out [planes,H/2,W/2]
 bool n3_down_supported(int H, int W, const void *in, const void *out, int dtype);
+// (C > 0: the INPUT is a channel slice with batch stride in_bstride elements; C == 0: dense)
 cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,
-                         int dtype, cudaStream_t s);
+                         int dtype, cudaStream_t s, int C = 0, long in_bstride = 0);
+
+// afr_small.cu -- N == 3 resamplers for small planes (a CTA stages a group of whole planes); plane p = (b, c)
+// lives at  base + b * bstride + c * plane_size  on the strided side (dense: C = 1, bstride = plane_size)
+// shapes served by the warp-shuffle whole-plane kernels (preferred over the strip kernels of afr_n3.cu); the
+// other small shapes use the shared-memory plane-group kernels only where the strip kernels cannot run
+bool warp_up_shape(int H, int W);
+bool warp_down_shape(int H, int W);
+bool small_up_supported(int H, int W, const void *in, const void *out, long out_bstride, int out_dtype);
+cudaError_t small_up_like(const void *in, void *out, long planes, int C, long out_bstride, int H, int W,
+                          const Taps3 &k, int in_dtype, int out_dtype, cudaStream_t s);
+bool small_down_supported(int H, int W, const void *in, const void *out, long in_bstride, int dtype);
+cudaError_t small_down_like(const void *in, void *out, long planes, int C, long in_bstride, int H, int W,
+                            const Taps3 &k, int dtype, cudaStream_t s);
 
 // afr_rotate.cu
 cudaError_t rotate_periodic_cubic(const float *x, float *y, long planes, int H, int W,

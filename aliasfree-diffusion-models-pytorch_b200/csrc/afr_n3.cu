@@ -27,6 +27,8 @@
 //           zero padding, mbarrier complete_tx), threads read rows from the staged chunk.
 #include <cuda.h>
 #include <cstdlib>
+#include <memory>
+#include <new>
 #include <type_traits>
 
 #include "afr_common.cuh"
@@ -69,28 +71,39 @@ __device__ __forceinline__ void up_odd_cols(const float (&xa)[6], const float (&
 // Activation on the mid rows.  fwd: u <- gelu(u) in place (g is unused, pass u twice).
 // bwd: g <- gelu'(u) * g.  Columns 1..8 form packed pairs; column 0 (X = 2j-1) is separate
 // because in shuffle mode it is normally taken from the left neighbour's column 8.
-template <bool kBwd>
-__device__ __forceinline__ void act_cols_1_8(float (&u)[9], float (&g)[9])
+// kLow: the bf16-grade polynomials of afr_common.cuh (kernels whose tensors are bf16).  The adjoint's
+// degree-4 S~ is a pure saving (4 packed FMAs per pair; its clamp exists in the fp32 form too).  The
+// forward's degree-4 P needs a clamp the degree-5 form does not (one FMNMX per element for one FFMA2 per
+// pair): AFR_BF16_LOW_FWD selects it (A/B builds).
+#ifndef AFR_BF16_LOW_FWD
+#define AFR_BF16_LOW_FWD 0
+#endif
+template <typename TO, bool kBwd> struct LowMath {
+    static constexpr bool value = sizeof(TO) == 2 && (kBwd || AFR_BF16_LOW_FWD);
+};
+template <bool kBwd, bool kLow>
+__device__ __forceinline__ void act_pair(float &ua, float &ub, float &ga, float &gb)
 {
-#pragma unroll
-    for (int c = 1; c < 9; c += 2) {
-        if (kBwd) gelu_grad_scaled_mul_x2(u[c], u[c + 1], g[c], g[c + 1]);
-        else gelu_erf_x2(u[c], u[c + 1]);
+    if (kBwd) {
+        if (kLow) gelu_grad_scaled_mul_low_x2(ua, ub, ga, gb);
+        else gelu_grad_scaled_mul_x2(ua, ub, ga, gb);
+    } else {
+        if (kLow) gelu_erf_low_x2(ua, ub);
+        else gelu_erf_x2(ua, ub);
     }
 }
 
-template <bool kBwd>
-__device__ __forceinline__ void act_col0_single(float (&u)[9], float (&g)[9])
+template <bool kBwd, bool kLow>
+__device__ __forceinline__ void act_cols_1_8(float (&u)[9], float (&g)[9])
 {
-    if (kBwd) g[0] *= gelu_grad_scaled(u[0]);
-    else u[0] = gelu_erf(u[0]);
+#pragma unroll
+    for (int c = 1; c < 9; c += 2) act_pair<kBwd, kLow>(u[c], u[c + 1], g[c], g[c + 1]);
 }
 
-template <bool kBwd>
+template <bool kBwd, bool kLow>
 __device__ __forceinline__ void act_col0_pair(float (&ue)[9], float (&uo)[9], float (&ge)[9], float (&go)[9])
 {
-    if (kBwd) gelu_grad_scaled_mul_x2(ue[0], uo[0], ge[0], go[0]);
-    else gelu_erf_x2(ue[0], uo[0]);
+    act_pair<kBwd, kLow>(ue[0], uo[0], ge[0], go[0]);
 }
 
 // ---------------------------------------------------------------------------------
@@ -136,6 +149,16 @@ struct GlobalRows {
     }
 };
 
+// The two halo columns (j-1 and j+4) are the neighbouring strips' c4.w / c4.x.  Read from the staged tile
+// as scalars (lane stride 16 bytes) each is a 4-way bank conflict: ncu counts 48 % of the kernel's shared
+// wavefronts as conflict replays.  AFR_HALO_SHFL=1 takes them from lane -1 / lane +1 by shuffle instead
+// (only lanes whose neighbour strip is not in the adjacent lane read the staged halo, conflict-free).
+// Measured on B200 (round 2, tools/ab_sweep.py): the shuffle form is 0-1.5 % SLOWER on every shape, fp32 and
+// bf16, forward and adjoint -- the LSU pipe is at 11 % and the kernel is issue-bound, so the replays are
+// hidden while two extra SHFL + two predicated LDS per row are not.  The scalar loads stay the default.
+#ifndef AFR_HALO_SHFL
+#define AFR_HALO_SHFL 0
+#endif
 template <typename T, bool kRes, bool kAff = false>
 struct TileRows {
     const T *x;   // shared tile, pointing at (tile row 0, this thread's column j)
@@ -143,11 +166,24 @@ struct TileRows {
     int pitch, row0;   // row0 = global row index of tile row 0
     int H;             // plane height (kAff: rows outside the plane must stay exactly zero)
     Affine f;
+    bool lds_l, lds_r; // this lane reads its left / right halo column from the tile (see above)
+    __device__ __forceinline__ void halo(const T *p, const float4 &c4, float &l, float &rr) const
+    {
+#if AFR_HALO_SHFL
+        l = __shfl_up_sync(0xffffffffu, c4.w, 1);
+        rr = __shfl_down_sync(0xffffffffu, c4.x, 1);
+        if (lds_l) l = lds1(p - 1);
+        if (lds_r) rr = lds1(p + 4);
+#else
+        l = lds1(p - 1); rr = lds1(p + 4);
+#endif
+    }
     __device__ __forceinline__ void load(int row, float (&v)[6]) const
     {
         const int off = (row - row0) * pitch;
         float4 c4 = lds4(x + off);
-        float l = lds1(x + off - 1), rr = lds1(x + off + 4);
+        float l, rr;
+        halo(x + off, c4, l, rr);
         if (kAff) {                                   // staged zeros (TMA OOB fill) times a stay zero
             const bool in = (unsigned)row < (unsigned)H;
             const float bc = in ? f.bc : 0.f, bl = in ? f.bl : 0.f, br = in ? f.br : 0.f;
@@ -156,9 +192,11 @@ struct TileRows {
             l = fmaf(l, f.a, bl); rr = fmaf(rr, f.a, br);
         }
         if (kRes) {
-            float4 q4 = lds4(r + off);
+            const float4 q4 = lds4(r + off);
+            float ql, qr;
+            halo(r + off, q4, ql, qr);
             c4.x += q4.x; c4.y += q4.y; c4.z += q4.z; c4.w += q4.w;
-            l += lds1(r + off - 1); rr += lds1(r + off + 4);
+            l += ql; rr += qr;
         }
         v[0] = l; v[1] = c4.x; v[2] = c4.y; v[3] = c4.z; v[4] = c4.w; v[5] = rr;
     }
@@ -208,6 +246,7 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
                                            bool store, bool first_col, bool any0, bool own0, const StepK &K,
                                            const RowSet &A, RowSet &B)
 {
+    constexpr bool kLow = LowMath<TO, kBwd>::value;
     const Taps3 &kU = K.kU, &kG = K.kG, &kB = K.kB;
     const float (&xa)[6] = A.x, (&da)[6] = A.d, (&mp)[9] = A.m;
     float (&xb)[6] = B.x, (&db)[6] = B.d, (&mo)[9] = B.m;
@@ -220,24 +259,24 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
         up_odd_cols<1>(xa, xb, kU, uo);
         up_even_cols<1>(da, kG, me);
         up_odd_cols<1>(da, db, kG, mo);
-        act_cols_1_8<true>(ue, me);
-        act_cols_1_8<true>(uo, mo);
+        act_cols_1_8<true, kLow>(ue, me);
+        act_cols_1_8<true, kLow>(uo, mo);
         if (any0 && own0) {      // any0 is warp-uniform: the common shapes skip with one uniform branch
             up_even_cols<0>(xa, kU, ue);
             up_odd_cols<0>(xa, xb, kU, uo);
             up_even_cols<0>(da, kG, me);
             up_odd_cols<0>(da, db, kG, mo);
-            act_col0_pair<true>(ue, uo, me, mo);
+            act_col0_pair<true, kLow>(ue, uo, me, mo);
         }
     } else {
         up_even_cols<1>(xa, kU, me);
         up_odd_cols<1>(xa, xb, kU, mo);
-        act_cols_1_8<false>(me, me);
-        act_cols_1_8<false>(mo, mo);
+        act_cols_1_8<false, kLow>(me, me);
+        act_cols_1_8<false, kLow>(mo, mo);
         if (any0 && own0) {      // any0 is warp-uniform: the common shapes skip with one uniform branch
             up_even_cols<0>(xa, kU, me);
             up_odd_cols<0>(xa, xb, kU, mo);
-            act_col0_pair<false>(me, mo, me, mo);
+            act_col0_pair<false, kLow>(me, mo, me, mo);
         }
     }
     const float le = __shfl_up_sync(0xffffffffu, me[8], 1), lo = __shfl_up_sync(0xffffffffu, mo[8], 1);
@@ -277,15 +316,24 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
 enum { PH_EE = 0, PH_EO = 1, PH_OE = 2, PH_OO = 3 };   // (mid row parity, mid column parity)
 struct SymK {
     float p[4][5];         // forward: Horner coefficients (degree 5 .. 1) of P(s_ph t) in -t; P(0) = -1
+                           // (bf16 kernels: degree 4 .. 1 in p[.][1..4], p[.][0] unused)
     float sw[4];           // adjoint: kappa * s_ph
     float dn[4];           // folded down taps by the phase class they read
+    float cl[4];           // bf16 forward: -T / s_ph, the clamp of -|xi| that keeps s_ph |xi| <= T
 };
 
-__device__ __forceinline__ void gelu_hat_x2(float &a, float &b, const float (&ca)[5], const float (&cb)[5])
+template <bool kLow>
+__device__ __forceinline__ void gelu_hat_x2(float &a, float &b, const float (&ca)[5], const float (&cb)[5],
+                                            float cla, float clb)
 {
-    const f32x2 sv = pack2(-fabsf(a), -fabsf(b));
-    f32x2 p = pack2(ca[0], cb[0]);
-    p = fma2(p, sv, pack2(ca[1], cb[1]));
+    f32x2 sv, p;
+    if (kLow) {
+        sv = pack2(fmaxf(-fabsf(a), cla), fmaxf(-fabsf(b), clb));
+        p = pack2(ca[1], cb[1]);
+    } else {
+        sv = pack2(-fabsf(a), -fabsf(b));
+        p = fma2(pack2(ca[0], cb[0]), sv, pack2(ca[1], cb[1]));
+    }
     p = fma2(p, sv, pack2(ca[2], cb[2]));
     p = fma2(p, sv, pack2(ca[3], cb[3]));
     p = fma2(p, sv, pack2(ca[4], cb[4]));
@@ -321,6 +369,7 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
                                            bool store, bool first_col, bool any0, bool own0, const SymK &K,
                                            const RowSet &A, RowSet &B)
 {
+    constexpr bool kLow = LowMath<TO, kBwd>::value;
     sx.load(i + 1, B.x);
     if (kBwd) sd.load(i + 1, B.d);
 #pragma unroll
@@ -339,29 +388,29 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
             ue[m] *= K.sw[(m & 1) ? PH_EE : PH_EO];
             uo[m] *= K.sw[(m & 1) ? PH_OE : PH_OO];
         }
-        act_cols_1_8<true>(ue, me);
-        act_cols_1_8<true>(uo, mo);
+        act_cols_1_8<true, kLow>(ue, me);
+        act_cols_1_8<true, kLow>(uo, mo);
         if (any0 && own0) {      // any0 is warp-uniform: the common shapes skip with one uniform branch
             sym_sums<0>(A.x, A.hx, B.x, B.hx, ue, uo);
             sym_sums<0>(A.d, A.hd, B.d, B.hd, me, mo);
             ue[0] *= K.sw[PH_EO];
             uo[0] *= K.sw[PH_OO];
-            act_col0_pair<true>(ue, uo, me, mo);
+            act_col0_pair<true, kLow>(ue, uo, me, mo);
             c0e = me[0]; c0o = mo[0];
         }
     } else {
         sym_sums<1>(A.x, A.hx, B.x, B.hx, me, mo);
-        gelu_hat_x2(me[1], me[3], K.p[PH_EE], K.p[PH_EE]);
-        gelu_hat_x2(me[5], me[7], K.p[PH_EE], K.p[PH_EE]);
-        gelu_hat_x2(me[2], me[4], K.p[PH_EO], K.p[PH_EO]);
-        gelu_hat_x2(me[6], me[8], K.p[PH_EO], K.p[PH_EO]);
-        gelu_hat_x2(mo[1], mo[3], K.p[PH_OE], K.p[PH_OE]);
-        gelu_hat_x2(mo[5], mo[7], K.p[PH_OE], K.p[PH_OE]);
-        gelu_hat_x2(mo[2], mo[4], K.p[PH_OO], K.p[PH_OO]);
-        gelu_hat_x2(mo[6], mo[8], K.p[PH_OO], K.p[PH_OO]);
+        gelu_hat_x2<kLow>(me[1], me[3], K.p[PH_EE], K.p[PH_EE], K.cl[PH_EE], K.cl[PH_EE]);
+        gelu_hat_x2<kLow>(me[5], me[7], K.p[PH_EE], K.p[PH_EE], K.cl[PH_EE], K.cl[PH_EE]);
+        gelu_hat_x2<kLow>(me[2], me[4], K.p[PH_EO], K.p[PH_EO], K.cl[PH_EO], K.cl[PH_EO]);
+        gelu_hat_x2<kLow>(me[6], me[8], K.p[PH_EO], K.p[PH_EO], K.cl[PH_EO], K.cl[PH_EO]);
+        gelu_hat_x2<kLow>(mo[1], mo[3], K.p[PH_OE], K.p[PH_OE], K.cl[PH_OE], K.cl[PH_OE]);
+        gelu_hat_x2<kLow>(mo[5], mo[7], K.p[PH_OE], K.p[PH_OE], K.cl[PH_OE], K.cl[PH_OE]);
+        gelu_hat_x2<kLow>(mo[2], mo[4], K.p[PH_OO], K.p[PH_OO], K.cl[PH_OO], K.cl[PH_OO]);
+        gelu_hat_x2<kLow>(mo[6], mo[8], K.p[PH_OO], K.p[PH_OO], K.cl[PH_OO], K.cl[PH_OO]);
         if (any0 && own0) {      // any0 is warp-uniform: the common shapes skip with one uniform branch
             sym_sums<0>(A.x, A.hx, B.x, B.hx, me, mo);
-            gelu_hat_x2(me[0], mo[0], K.p[PH_EO], K.p[PH_OO]);
+            gelu_hat_x2<kLow>(me[0], mo[0], K.p[PH_EO], K.p[PH_OO], K.cl[PH_EO], K.cl[PH_OO]);
             c0e = me[0]; c0o = mo[0];
         }
     }
@@ -736,6 +785,9 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     // warp that does not start a plane row recomputes column 0 itself
     const bool any0 = cfg.own0_any != 0;
     const bool own0 = any0 && (cfg.ghost == 0) && (j > 0) && (s == 0 || (threadIdx.x & 31) == 0);
+    // halo columns: from the adjacent lane unless that lane holds another plane row / tile / warp
+    const bool lds_l = (s == 0) || ((threadIdx.x & 31) == 0);
+    const bool lds_r = (s == cfg.strips - 1) || ((threadIdx.x & 31) == 31);
     const int toff = pl * rows * pitch + HALO + 4 * s;
     T *dst = out + (p0 + pl) * (long)H * W + (valid ? j : 0);
     const Affine aff = make_affine(kAff ? scale : nullptr, shift, p0 + pl, p0 + pl < planes, j, W);
@@ -753,8 +805,8 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
         const int r0 = istart + k * cfg.R;
         mbar_wait(&full[k & 1], (k >> 1) & 1);
         if (k == 0) {
-            TileRows<T, kRes, kAff> sx{xs + toff, rs + toff, pitch, r0, H, aff};
-            TileRows<T, false> sd{ds + toff, nullptr, pitch, r0, H, Affine{0.f, 0.f, 0.f, 0.f}};
+            TileRows<T, kRes, kAff> sx{xs + toff, rs + toff, pitch, r0, H, aff, lds_l, lds_r};
+            TileRows<T, false> sd{ds + toff, nullptr, pitch, r0, H, Affine{0.f, 0.f, 0.f, 0.f}, lds_l, lds_r};
             strip_begin<kBwd, KT>(sx, sd, r0, S0);
         }
         // R is even: register roles return to S0.  The last chunk stops after the segment's last row
@@ -769,14 +821,14 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
             constexpr bool kInside = decltype(inside)::value;
             for (int i = r0; i < rend; i += 2) {
                 {
-                    TileRows<T, kRes, kAff> sx{xr, rr, pitch, i + 1, H, aff};
-                    TileRows<T, false> sd{dr, nullptr, pitch, i + 1, H, Affine{0.f, 0.f, 0.f, 0.f}};
+                    TileRows<T, kRes, kAff> sx{xr, rr, pitch, i + 1, H, aff, lds_l, lds_r};
+                    TileRows<T, false> sd{dr, nullptr, pitch, i + 1, H, Affine{0.f, 0.f, 0.f, 0.f}, lds_l, lds_r};
                     strip_step<kBwd>(sx, sd, orow, i, kInside ? valid : (valid && i >= seg_lo && i < seg_hi), first_col,
                                      any0, own0, K, S0, S1);
                 }
                 {
-                    TileRows<T, kRes, kAff> sx{xr + pitch, rr + pitch, pitch, i + 2, H, aff};
-                    TileRows<T, false> sd{dr + pitch, nullptr, pitch, i + 2, H, Affine{0.f, 0.f, 0.f, 0.f}};
+                    TileRows<T, kRes, kAff> sx{xr + pitch, rr + pitch, pitch, i + 2, H, aff, lds_l, lds_r};
+                    TileRows<T, false> sd{dr + pitch, nullptr, pitch, i + 2, H, Affine{0.f, 0.f, 0.f, 0.f}, lds_l, lds_r};
                     strip_step<kBwd>(sx, sd, orow + W, i + 1,
                                      kInside ? valid : (valid && i + 1 >= seg_lo && i + 1 < seg_hi), first_col, any0,
                                      own0, K, S1, S0);
@@ -799,7 +851,7 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 up3_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int H, int W, int strips,
-           int nseg, int R, const __grid_constant__ Taps3 k)
+           int nseg, int R, int C, long out_bstride, const __grid_constant__ Taps3 k)
 {
     const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const long per_plane = (long)strips * nseg;
@@ -809,7 +861,7 @@ up3_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int H, 
     const long p = idx / per_plane;
     const int j = 4 * s, i0 = seg * R, i1 = min(H, i0 + R);
     const TI *src = in + p * (long)H * W + j;
-    TO *dst = out + p * 4L * H * W + 2 * j;
+    TO *dst = out + strided_base((unsigned)p, C, out_bstride, 4L * H * W) + 2 * j;   // C == 0: dense output
     const int W2 = 2 * W;
     const bool has_r = (j + 4 < W);
 
@@ -918,7 +970,7 @@ __device__ __forceinline__ void load_down_row(const T *plane, int row, int H, in
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
 down3_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, int W, int Ho,
-             int Wo, int strips, int nseg, int R, const __grid_constant__ Taps3 k)
+             int Wo, int strips, int nseg, int R, int C, long in_bstride, const __grid_constant__ Taps3 k)
 {
     const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const long per_plane = (long)strips * nseg;
@@ -927,7 +979,7 @@ down3_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, 
     const int seg = (int)((idx / strips) % nseg);
     const long p = idx / per_plane;
     const int j = V * s, i0 = seg * R, i1 = min(Ho, i0 + R);
-    const T *plane = in + p * (long)H * W;
+    const T *plane = in + strided_base((unsigned)p, C, in_bstride, (long)H * W);      // C == 0: dense input
     T *dst = out + p * (long)Ho * Wo + j;
     const bool has_l = (j > 0);
 
@@ -1089,8 +1141,36 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-static bool make_plane_map(CUtensorMap *m, const void *base, long planes, int H, int W, int dtype,
-                           int box_w, int box_h, int box_p)
+// A tensor map encodes nothing but (base address, shape, strides, box, element type): the same key always
+// yields the same 128 bytes, whatever has happened to the allocation in between.  PyTorch's caching allocator
+// hands the same addresses back step after step, so the descriptors of a UNet's ~50 fused launches are
+// encoded once and then found in this per-thread, direct-mapped cache (no locks; the library keeps no other
+// state -- SURVEY.md section 8b).  AFR_NO_DESC_CACHE=1 disables it (A/B timing).
+struct MapKey {
+    const void *base;
+    long planes;
+    int H, W, dtype, bw, bh, bp;
+    bool operator==(const MapKey &o) const
+    {
+        return base == o.base && planes == o.planes && H == o.H && W == o.W && dtype == o.dtype && bw == o.bw &&
+               bh == o.bh && bp == o.bp;
+    }
+};
+struct MapSlot {
+    MapKey key;
+    CUtensorMap map;
+    bool valid;
+};
+static constexpr int kMapSlots = 512;
+
+static bool desc_cache_disabled()
+{
+    static const bool v = []() { const char *e = getenv("AFR_NO_DESC_CACHE"); return e && atoi(e) != 0; }();
+    return v;
+}
+
+static bool encode_plane_map(CUtensorMap *m, const void *base, long planes, int H, int W, int dtype,
+                             int box_w, int box_h, int box_p)
 {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { set_detail("cuTensorMapEncodeTiled entry point not found"); return false; }
@@ -1114,6 +1194,26 @@ static bool make_plane_map(CUtensorMap *m, const void *base, long planes, int H,
         set_detail("cuTensorMapEncodeTiled failed (CUresult %d) base=%p dims=[%d,%d,%ld] box=[%d,%d,%d]", (int)r,
                    base, W, H, planes, box_w, box_h, box_p);
     return r == CUDA_SUCCESS;
+}
+
+static bool make_plane_map(CUtensorMap *m, const void *base, long planes, int H, int W, int dtype,
+                           int box_w, int box_h, int box_p)
+{
+    if (desc_cache_disabled()) return encode_plane_map(m, base, planes, H, W, dtype, box_w, box_h, box_p);
+    // allocated on a thread's first TMA launch, freed with the thread (over-aligned type: aligned operator new)
+    static thread_local std::unique_ptr<MapSlot[]> slots;
+    if (!slots) slots.reset(new (std::nothrow) MapSlot[kMapSlots]());
+    if (!slots) return encode_plane_map(m, base, planes, H, W, dtype, box_w, box_h, box_p);
+    const MapKey key = {base, planes, H, W, dtype, box_w, box_h, box_p};
+    uint64_t h = (uint64_t)reinterpret_cast<uintptr_t>(base) >> 8;     // allocations are 512-byte aligned
+    h ^= (uint64_t)planes * 0x9E3779B97F4A7C15ull;
+    h ^= ((uint64_t)H << 40) ^ ((uint64_t)W << 20) ^ ((uint64_t)box_h << 8) ^ (uint64_t)box_p ^ ((uint64_t)dtype << 60);
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    MapSlot &sl = slots[h % kMapSlots];
+    if (sl.valid && sl.key == key) { *m = sl.map; return true; }
+    if (!encode_plane_map(m, base, planes, H, W, dtype, box_w, box_h, box_p)) return false;
+    sl.key = key; sl.map = *m; sl.valid = true;
+    return true;
 }
 
 static inline int pick_rows(int H) { return H < 8 ? H : 8; }
@@ -1261,12 +1361,14 @@ static void phase_taps(const Taps3 &t, double (&s)[4])
 
 // false: the taps do not qualify (asymmetric, or a negative / non-finite up tap in the forward,
 // where gelu(s xi) = s ghat(xi) needs s >= 0) and the general kernels run instead
-static bool make_sym(const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd, SymK *K)
+static bool make_sym(const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd, bool low, SymK *K)
 {
     if (!d4_symmetric(kU) || !d4_symmetric(kB) || (bwd && !d4_symmetric(kG))) return false;
     double su[4], sb[4], sg[4];
     phase_taps(kU, su); phase_taps(kB, sb); phase_taps(kG, sg);
-    static const double P[5] = {-(double)AFR_P5, (double)AFR_P4, -(double)AFR_P3, (double)AFR_P2, -(double)AFR_P1};
+    static const double P5[5] = {-(double)AFR_P5, (double)AFR_P4, -(double)AFR_P3, (double)AFR_P2, -(double)AFR_P1};
+    static const double P4[5] = {0.0, (double)AFR_Q4, -(double)AFR_Q3, (double)AFR_Q2, -(double)AFR_Q1};
+    const double *P = low ? P4 : P5;      // bf16 tensors: the degree-4 form, |xi| clamped to T / s_ph
     for (int ph = 0; ph < 4; ++ph) {
         if (!bwd && !(su[ph] >= 0.0 && su[ph] < 1e30)) return false;
         double pw = su[ph] * su[ph] * su[ph] * su[ph] * su[ph];          // s^5 .. s^1
@@ -1274,6 +1376,7 @@ static bool make_sym(const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd
             K->p[ph][k] = (float)(P[k] * pw);
             pw = su[ph] != 0.0 ? pw / su[ph] : 0.0;
         }
+        K->cl[ph] = su[ph] > 0.0 ? (float)(-(double)AFR_LOW_T / su[ph]) : -3.0e38f;
         K->sw[ph] = (float)su[ph];                                       // adjoint: kU arrives kappa-scaled
         K->dn[ph] = (float)(sb[ph] * (bwd ? sg[ph] : su[ph]));
     }
@@ -1298,7 +1401,7 @@ cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, const float
     if (bwd && scale) { set_detail("affine fusion is forward-only"); return cudaErrorNotSupported; }
     SymK KS;
     const StepK KG = {kU, kG, kB};
-    const bool sym = allow_sym && make_sym(kU, kG, kB, bwd, &KS);
+    const bool sym = allow_sym && make_sym(kU, kG, kB, bwd, dtype == AFR_BF16 && AFR_BF16_LOW_FWD, &KS);
     if (kernel_name)
         *kernel_name = use_tma ? (sym ? "fgelu3_tma_kernel<sym>" : "fgelu3_tma_kernel")
                                : (sym ? "fgelu3_direct_kernel<sym>" : "fgelu3_direct_kernel");
@@ -1315,14 +1418,15 @@ bool n3_up_supported(int H, int W, const void *in, const void *out, int in_dtype
 }
 
 cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,
-                       int in_dtype, int out_dtype, cudaStream_t s)
+                       int in_dtype, int out_dtype, cudaStream_t s, int C, long out_bstride)
 {
+    if (planes > 0x7fffffffL) return cudaErrorInvalidConfiguration;
     const int strips = W / 4, R = pick_rows(H), nseg = (H + R - 1) / R;
     const long total = planes * (long)strips * nseg;
     const long grid = (total + 255) / 256;
     if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
     // bf16 input only: with fp32 input the up-front loads are 15-60 % slower than the row loop (measured)
-    const bool short_plane = (H == 4 || H == 8) && in_dtype == AFR_BF16 && !plane_kernels_disabled();
+    const bool short_plane = (H == 4 || H == 8) && in_dtype == AFR_BF16 && !plane_kernels_disabled() && C == 0;
     const long sgrid = (planes * strips + 255) / 256;
 #define AFR_UP(TI, TO)                                                                                       \
     do {                                                                                                     \
@@ -1332,7 +1436,7 @@ cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, con
             up3_short_kernel<TI, TO, 8><<<(unsigned)sgrid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, W, strips, k); \
         else                                                                                                 \
             up3_kernel<TI, TO><<<(unsigned)grid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, H, W,        \
-                                                              strips, nseg, R, k);                           \
+                                                              strips, nseg, R, C, out_bstride, k);           \
     } while (0)
     if (in_dtype == AFR_F32 && out_dtype == AFR_F32) AFR_UP(float, float);
     else if (in_dtype == AFR_BF16 && out_dtype == AFR_BF16) AFR_UP(bf16, bf16);
@@ -1349,8 +1453,9 @@ bool n3_down_supported(int H, int W, const void *in, const void *out, int dtype)
 }
 
 cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, const Taps3 &k,
-                         int dtype, cudaStream_t s)
+                         int dtype, cudaStream_t s, int C, long in_bstride)
 {
+    if (planes > 0x7fffffffL) return cudaErrorInvalidConfiguration;
     const int Ho = (H + 1) / 2, Wo = W / 2;
     // bf16: 8 outputs per thread when the row width and the bases allow 128-bit vectors both ways
     const bool wide = dtype == AFR_BF16 && (Wo % 8) == 0 && aligned_to(in, 16) && aligned_to(out, 16);
@@ -1359,7 +1464,7 @@ cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, c
     const long total = planes * (long)strips * nseg;
     const long grid = (total + 255) / 256;
     if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
-    if (H == 8 && dtype == AFR_BF16 && !plane_kernels_disabled()) {   // short bf16 planes: all rows up front, unrolled (+16 %; fp32: no gain)
+    if (H == 8 && dtype == AFR_BF16 && !plane_kernels_disabled() && C == 0) {   // short bf16 planes: all rows up front, unrolled (+16 %; fp32: no gain)
         const int sstrips = Wo / 4;
         const long sgrid = (planes * sstrips + 255) / 256;
         if (sgrid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
@@ -1368,13 +1473,13 @@ cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, c
     }
     if (dtype == AFR_F32)
         down3_kernel<float, 4><<<(unsigned)grid, 256, 0, s>>>((const float *)in, (float *)out, planes,
-                                                              H, W, Ho, Wo, strips, nseg, R, k);
+                                                              H, W, Ho, Wo, strips, nseg, R, C, in_bstride, k);
     else if (wide)
         down3_kernel<bf16, 8><<<(unsigned)grid, 256, 0, s>>>((const bf16 *)in, (bf16 *)out, planes, H,
-                                                             W, Ho, Wo, strips, nseg, R, k);
+                                                             W, Ho, Wo, strips, nseg, R, C, in_bstride, k);
     else
         down3_kernel<bf16, 4><<<(unsigned)grid, 256, 0, s>>>((const bf16 *)in, (bf16 *)out, planes, H,
-                                                             W, Ho, Wo, strips, nseg, R, k);
+                                                             W, Ho, Wo, strips, nseg, R, C, in_bstride, k);
     return cudaGetLastError();
 }
 

@@ -168,6 +168,47 @@ class _FilteredGelu(torch.autograd.Function):
         return dx, (dx if ctx.has_res else None), None, None
 
 
+class _Up2xCat(torch.autograd.Function):
+    """``torch.cat([skip, up2x(x)], dim=1)`` with the upsampler writing its result straight into the
+    channel slice of the concatenated buffer (and its adjoint reading the gradient slice in place)."""
+
+    @staticmethod
+    def forward(ctx, skip, x, k):
+        B, C, H, W = x.shape
+        Cs = skip.shape[1]
+        out = torch.empty((B, Cs + C, 2 * H, 2 * W), dtype=skip.dtype, device=skip.device)
+        out[:, :Cs].copy_(skip)
+        with torch.cuda.device(x.device):
+            _check(_native.lib().afr_up2x_fwd_strided(x.data_ptr(), out[:, Cs:].data_ptr(), B, C, H, W, out.stride(0),
+                                                      k.ptr, k.n, _DT[x.dtype], _DT[out.dtype], _stream(x)))
+        ctx.k, ctx.shape, ctx.cs, ctx.in_dtype = k, (B, C, H, W), Cs, x.dtype
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        B, C, H, W = ctx.shape
+        g = g.contiguous()
+        dx = torch.empty((B, C, H, W), dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            _check(_native.lib().afr_up2x_bwd_strided(g[:, ctx.cs:].data_ptr(), dx.data_ptr(), B, C, H, W, g.stride(0),
+                                                      ctx.k.ptr, ctx.k.n, _DT[g.dtype], _stream(g)))
+        return g[:, :ctx.cs], dx.to(ctx.in_dtype), None
+
+
+def up2x_cat(skip, x, filt):
+    """``torch.cat([skip, custom_upsample(x, filt)], dim=1)`` (modules/ddpm_utils.py:344-345, 413-414) without
+    materialising the upsampled tensor separately: saves one read and one write of it.  Shapes the strided
+    kernels do not cover (N != 3, W % 4 != 0, a forced kernel path) take the two-step form."""
+    x, skip = _require(x), _require(skip, "skip_x")
+    k = _taps(filt)
+    B, C, H, W = x.shape
+    if (k.n == 3 and W % 4 == 0 and skip.shape[0] == B and tuple(skip.shape[2:]) == (2 * H, 2 * W)
+            and (skip.shape[1] * 4 * H * W * skip.element_size()) % 32 == 0 and _native.PATHS_AUTO()):
+        return _Up2xCat.apply(skip, x, k)
+    return torch.cat([skip, _Up2x.apply(x, k, skip.dtype)], dim=1)
+
+
 def _match_residual(x, residual):
     """``x + residual`` follows PyTorch type promotion (e.g. bf16 conv output + fp32 skip under
     autocast -> fp32), like the reference's ``x = x + residual`` (modules/ddpm_utils.py:128)."""

@@ -80,6 +80,21 @@ int afr_up2x_fwd(const void *x, void *u, int B, int C, int H, int W,
 int afr_up2x_bwd(const void *du, void *dx, int B, int C, int H, int W,
                  const float *taps, int N, int du_dtype, int dx_dtype, void *stream);
 
+/* custom_upsample writing straight into a channel slice of a larger tensor -- the second half of the
+ * `torch.cat([skip_x, x], dim=1)` buffer of Up_FF / Up_FFF (modules/ddpm_utils.py:344-345, 414), which saves
+ * one read and one write of the upsampled tensor.  `u` points at element (b=0, c=0) of the slice inside the
+ * destination; `out_batch_stride` is the destination's batch stride in ELEMENTS (>= C*2H*2W, 16-byte
+ * multiples); channel, row and column strides are dense.  N == 3, W % 4 == 0 and a 32-byte aligned slice
+ * base / batch stride are required: AFR_ERR_UNSUPPORTED otherwise (callers fall back to afr_up2x_fwd + a
+ * copy). */
+int afr_up2x_fwd_strided(const void *x, void *u, int B, int C, int H, int W, int64_t out_batch_stride,
+                         const float *taps, int N, int in_dtype, int out_dtype, void *stream);
+
+/* adjoint of the above: du is a channel slice (batch stride `du_batch_stride` elements) of the gradient of
+ * the concatenated tensor; dx [B,C,H,W] dense.  Same restrictions. */
+int afr_up2x_bwd_strided(const void *du, void *dx, int B, int C, int H, int W, int64_t du_batch_stride,
+                         const float *taps, int N, int dtype, void *stream);
+
 /* custom_downsample(x, jinc_filter, factor=2)          modules/filtrs.py:71-77
  * v [B,C,H,W] -> y [B,C,ceil(H/2),ceil(W/2)], contiguous (the reference returns a
  * strided view of the full-resolution convolution; values are identical). */

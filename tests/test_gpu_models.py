@@ -113,17 +113,17 @@ def test_blocks_in_fp64_with_only_the_afr_ops_swapped(afr, oracle, tag):
             return torch.from_numpy(oracle.down2x_bwd(np32(dd), ctx.k, *ctx.hw)).double(), None
 
     taps = lambda f: (f.t if isinstance(f, afr.Taps) else torch.as_tensor(f)).numpy().astype(np.float32)
-    real = {n: getattr(afr.ops, n) for n in ("filtered_gelu", "up2x", "custom_downsample")}
+    real = {n: getattr(afr.ops, n) for n in ("filtered_gelu", "up2x_cat", "custom_downsample")}
     gpu = lambda v: v.float().cuda()
     sides = {
         "ours": dict(
             filtered_gelu=lambda x, fu, fd, residual=None: real["filtered_gelu"](
                 gpu(x), fu, fd, residual=None if residual is None else gpu(residual)).cpu().double(),
-            up2x=lambda x, f, out_dtype=None: real["up2x"](gpu(x), f).cpu().double(),
+            up2x_cat=lambda skip, x, f: real["up2x_cat"](gpu(skip), gpu(x), f).cpu().double(),
             custom_downsample=lambda x, f, factor=2: real["custom_downsample"](gpu(x), f).cpu().double()),
         "oracle": dict(
             filtered_gelu=lambda x, fu, fd, residual=None: OFused.apply(x, residual, taps(fu), taps(fd)),
-            up2x=lambda x, f, out_dtype=None: OUp.apply(x, taps(f)),
+            up2x_cat=lambda skip, x, f: torch.cat([skip, OUp.apply(x, taps(f))], dim=1),
             custom_downsample=lambda x, f, factor=2: ODown.apply(x, taps(f))),
     }
     res = {}

@@ -378,6 +378,93 @@ def test_oracle_bf16_every_n3_family_fwd_and_adjoint(afr, oracle, shape, path):
         afr.set_path("auto")
 
 
+SMALL_SHAPES = [(3, 5, 4, 4), (2, 3, 8, 8), (2, 2, 16, 16), (1, 3, 4, 8), (2, 2, 12, 4), (1, 2, 7, 8), (1, 1, 1, 4),
+                (40, 37, 4, 4), (1, 2, 2, 64), (300, 3, 8, 8), (5, 1, 8, 4), (3, 3, 16, 8), (2, 5, 2, 4), (7, 3, 32, 4),
+                (1, 7, 8, 16)]
+WARP_UP = {(4, 4), (8, 8), (8, 4), (4, 8), (2, 4), (2, 8), (16, 8), (16, 4)}
+WARP_DOWN = {(4, 4), (8, 8), (16, 16), (8, 4), (4, 8), (16, 8), (8, 16), (2, 4), (32, 4), (16, 4)}
+
+
+def _up_kernel_name(h, w):
+    return "up3_warp_kernel" if (h, w) in WARP_UP else "up3_kernel"
+
+
+def _down_kernel_name(h, w):
+    if (h, w) in WARP_DOWN:
+        return "down3_warp_kernel"
+    return "down3_kernel" if w % 8 == 0 else "down3_group_kernel"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("shape", SMALL_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_small_plane_kernels(afr, oracle, shape, dtype):
+    """The resamplers that serve the UNet's inner levels (afr_small.cu): warp-shuffle whole-plane kernels for
+    planes that fit a warp, the plane-group kernel for 4-wide planes the strip kernels cannot take.  Both
+    directions and both adjoints, asymmetric taps, odd heights, plane counts that leave partial warps / groups."""
+    B, C, H, W = shape
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    rng = np.random.default_rng(H * 100 + W + B)
+    k = (oracle.lowpass_taps(np.pi / 2, 3, 2.0) + 0.03 * rng.standard_normal((3, 3))).astype(np.float32)
+    kt = afr.Taps(k)
+    x = dev(rng.standard_normal(shape).astype(np.float32), dtype)
+    x32 = host(x)
+    u = afr.ops._up_fwd(x, kt, dtype)
+    assert afr.last_kernel() == _up_kernel_name(H, W)
+    assert relmax(host(u), oracle.up2x(x32, k)) <= tol
+    du = dev(rng.standard_normal(tuple(u.shape)).astype(np.float32), dtype)
+    gx = afr.ops._up_bwd(du, kt, H, W)
+    assert afr.last_kernel() == _down_kernel_name(2 * H, 2 * W)
+    assert relmax(host(gx), oracle.up2x_bwd(host(du), k)) <= tol
+    d = afr.ops._down_fwd(x, kt)
+    assert afr.last_kernel() == _down_kernel_name(H, W)
+    assert tuple(d.shape) == (B, C, (H + 1) // 2, W // 2)
+    assert relmax(host(d), oracle.down2x(x32, k)) <= tol
+    dd = dev(rng.standard_normal(tuple(d.shape)).astype(np.float32), dtype)
+    gx = afr.ops._down_bwd(dd, kt, H, W)
+    if H % 2 == 0:
+        assert afr.last_kernel() == _up_kernel_name(H // 2, W // 2) or W // 2 < 4
+    assert relmax(host(gx), oracle.down2x_bwd(host(dd), k, H, W)) <= tol
+    if dtype == torch.bfloat16:
+        assert relmax(host(afr.custom_upsample(x, k)), oracle.up2x(x32, k)) <= FP32_TOL     # bf16 in, fp32 out
+    # autograd wiring of the same calls
+    xt = x.clone().requires_grad_(True)
+    (g1,) = torch.autograd.grad(afr.up2x(xt, k), xt, du)
+    assert relmax(host(g1), oracle.up2x_bwd(host(du), k)) <= tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("shape,cs", [((3, 8, 4, 4), 8), ((2, 4, 8, 8), 6), ((2, 2, 16, 16), 2), ((1, 3, 4, 8), 1)])
+def test_up2x_cat_writes_into_the_concat_buffer(afr, oracle, shape, cs, dtype):
+    """torch.cat([skip, custom_upsample(x)], 1) with the upsampler writing its channel slice in place, and the
+    adjoint reading the gradient slice in place (modules/ddpm_utils.py:413-414)."""
+    B, C, H, W = shape
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    rng = np.random.default_rng(C + H)
+    k = oracle.lowpass_taps(np.pi / 2, 3, 2.0)
+    x = dev(rng.standard_normal(shape).astype(np.float32), dtype).requires_grad_(True)
+    skip = dev(rng.standard_normal((B, cs, 2 * H, 2 * W)).astype(np.float32), dtype).requires_grad_(True)
+    n0 = afr.launch_count()
+    out = afr.up2x_cat(skip, x, k)
+    assert afr.launch_count() == n0 + 1 and afr.last_kernel() == _up_kernel_name(H, W)
+    assert tuple(out.shape) == (B, cs + C, 2 * H, 2 * W) and out.is_contiguous()
+    assert torch.equal(out[:, :cs], skip)
+    assert relmax(host(out[:, cs:]), oracle.up2x(host(x), k)) <= tol
+    g = dev(rng.standard_normal(tuple(out.shape)).astype(np.float32), dtype)
+    gs, gx = torch.autograd.grad(out, (skip, x), g)
+    assert torch.equal(gs, g[:, :cs])
+    assert relmax(host(gx), oracle.up2x_bwd(host(g[:, cs:]), k)) <= tol
+    # larger planes go through the strip kernels with the same slice addressing; shapes the strided kernels do
+    # not cover (here: an odd width) take the two-step form -- identical values either way
+    for hw in ((32, 32), (6, 5)):
+        xb = dev(rng.standard_normal((2, 2) + hw).astype(np.float32), dtype).requires_grad_(True)
+        sb = dev(rng.standard_normal((2, 4, 2 * hw[0], 2 * hw[1])).astype(np.float32), dtype)
+        big = afr.up2x_cat(sb, xb, k)
+        assert torch.equal(big[:, :4], sb) and relmax(host(big[:, 4:]), oracle.up2x(host(xb), k)) <= tol
+        gb = dev(rng.standard_normal(tuple(big.shape)).astype(np.float32), dtype)
+        (gxb,) = torch.autograd.grad(big, xb, gb)
+        assert relmax(host(gxb), oracle.up2x_bwd(host(gb[:, 4:]), k)) <= tol
+
+
 def test_kernel_selection(afr):
     k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
     afr.filtered_gelu(torch.randn(2, 2, 32, 32, device="cuda"), k, k)
