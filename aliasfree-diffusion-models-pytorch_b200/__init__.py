@@ -5,7 +5,7 @@ The package directory is ``aliasfree-diffusion-models-pytorch_b200/``; import it
 """
 from . import _native
 from .filters import circularLowpassKernel, taps_from_settings
-from .ops import (Taps, custom_downsample, custom_upsample, ddpm_update_, down2x, filtered_gelu,
+from .ops import (Taps, custom_downsample, custom_upsample, ddpm_update_, down2x, filtered_gelu, gelu_down2x,
                   rotate, up2x, up2x_cat)
 from .blocks import (DoubleConv, DoubleConv_F, DoubleConv_F4, Down, Down_F, Down_F4, Down_FF, Down_FFF,
                      SelfAttention, Up, Up_F, Up_F4, Up_FF, Up_FFF)
@@ -22,7 +22,7 @@ last_kernel = _native.last_kernel
 launch_count = _native.launch_count
 
 __all__ = ["circularLowpassKernel", "taps_from_settings", "Taps", "custom_upsample",
-           "custom_downsample", "up2x", "down2x", "up2x_cat", "filtered_gelu", "rotate", "ddpm_update_",
+           "custom_downsample", "up2x", "down2x", "up2x_cat", "filtered_gelu", "gelu_down2x", "rotate", "ddpm_update_",
            "DoubleConv", "DoubleConv_F", "DoubleConv_F4", "Down", "Down_F", "Down_F4", "Down_FF", "Down_FFF",
            "Up", "Up_F", "Up_F4",
            "Up_FF", "Up_FFF", "SelfAttention", "UNet", "Diffusion", "patch", "unpatch", "parallel", "rotation_results", "shift_results", "HostPipeline",

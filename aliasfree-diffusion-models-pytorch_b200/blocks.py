@@ -13,6 +13,8 @@ fused CUDA kernel (ops.filtered_gelu), the residual add of the second activation
 into that launch, and the standalone resamplers are single kernels as well; the 3x3
 convolutions, GroupNorm and attention stay on cuDNN / cuBLAS.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -21,9 +23,12 @@ from . import ops
 from .filters import taps_from_settings
 
 
-# Inference (no-grad) forward of DoubleConv_F folds each GroupNorm's normalise + affine into the
-# fused activation kernel that follows it; set to False to always run nn.GroupNorm separately.
-FUSE_GROUPNORM_INFERENCE = True
+# DoubleConv_F folds each GroupNorm's normalise + affine into the kernel that follows it -- the fused
+# activation kernel, or the stage's embedding add -- in inference AND training;
+# set to False to always run nn.GroupNorm separately.  (FUSE_GROUPNORM_INFERENCE: variant 4's
+# inference-only fold.)
+FUSE_GROUPNORM = os.environ.get("AFR_FUSE_GROUPNORM", "1") != "0"
+FUSE_GROUPNORM_INFERENCE = FUSE_GROUPNORM
 
 
 def _groupnorm1_affine(h, norm):
@@ -94,27 +99,26 @@ class DoubleConv_F(nn.Module):
             self._taps = (key, ops.Taps(self.sinc_filter), ops.Taps(self.jinc_filter))
         return self._taps[1], self._taps[2]
 
-    def _can_fuse_norm(self, x):
-        return (FUSE_GROUPNORM_INFERENCE and not torch.is_grad_enabled() and x.is_cuda and up_is_n3(self)
-                and x.shape[-1] % 4 == 0 and x.dtype in (torch.float32, torch.bfloat16)
-                and self.norm1.num_groups == 1 and self.norm1.affine)
-
-    def forward(self, x):
+    def forward(self, x, emb=None):
+        """``emb`` ([B, out_channels], optional, non-residual blocks only): the stage's time embedding, added to
+        the output (``+ emb[:, :, None, None]``) inside the last GroupNorm's apply pass."""
         up, dn = self._filters()
-        if self._can_fuse_norm(x):
-            # inference: GroupNorm statistics by torch, normalise + affine inside the activation kernel
-            h = self.conv1(x)
-            h = ops.filtered_gelu_affine(h, *_groupnorm1_affine(h, self.norm1), up, dn)
-            h = self.conv2(h)
-            if self.residual:
-                return ops.filtered_gelu_affine(h, *_groupnorm1_affine(h, self.norm2), up, dn, residual=x)
-            return self.norm2(h)
-        h = self.norm1(self.conv1(x))
-        h = ops.filtered_gelu(h, up, dn)
-        h = self.norm2(self.conv2(h))
+        nu, nd = self.sinc_filter.shape[-1], self.jinc_filter.shape[-1]
+        h = self.conv1(x)
+        if FUSE_GROUPNORM and ops.norm_fusable(h, self.norm1, nu, nd):
+            h = ops.norm_filtered_gelu(h, self.norm1, up, dn)      # norm1 folded into the activation kernel
+        else:
+            h = ops.filtered_gelu(self.norm1(h), up, dn)
+        h = self.conv2(h)
         if self.residual:
-            h = ops.filtered_gelu(h, up, dn, residual=x)     # gelu-filter(x + h), add fused
-        return h
+            if FUSE_GROUPNORM and ops.norm_fusable(h, self.norm2, nu, nd) and x.dtype == h.dtype:
+                return ops.norm_filtered_gelu(h, self.norm2, up, dn, residual=x)
+            return ops.filtered_gelu(self.norm2(h), up, dn, residual=x)     # gelu-filter(x + h), add fused
+        if emb is not None:
+            if FUSE_GROUPNORM and ops.norm_fusable(h, self.norm2) and emb.dtype == h.dtype:
+                return ops.norm_add_emb(h, self.norm2, emb)
+            return self.norm2(h) + emb[:, :, None, None]
+        return self.norm2(h)
 
 
 def up_is_n3(block):
@@ -129,6 +133,14 @@ class _TimeConditioned(nn.Module):
 
     def _add_emb(self, x, t):
         return x + self.emb_layer(t)[:, :, None, None]
+
+    def _blocks_then_emb(self, first, last, x, t):
+        """The stage's two DoubleConv blocks and the embedding add; filtered blocks take the embedding into their
+        last GroupNorm's apply pass (no broadcast tensor, no separate add)."""
+        h = first(x)
+        if type(last) is DoubleConv_F:
+            return last(h, emb=self.emb_layer(t))
+        return self._add_emb(last(h), t)
 
 
 def _pair(block, cin, cout, mid=None, **kw):
@@ -172,7 +184,7 @@ class Down_F(_TimeConditioned):
         self._make_emb(emb_dim, out_channels)
 
     def forward(self, x, t):
-        return self._add_emb(self.maxpool_conv(x), t)
+        return self._blocks_then_emb(self.maxpool_conv[1], self.maxpool_conv[2], self.maxpool_conv[0](x), t)
 
 
 class Up_F(_TimeConditioned):
@@ -186,7 +198,7 @@ class Up_F(_TimeConditioned):
         self._make_emb(emb_dim, out_channels)
 
     def forward(self, x, skip_x, t):
-        return self._add_emb(self.conv(torch.cat([skip_x, self.up(x)], dim=1)), t)
+        return self._blocks_then_emb(self.conv[0], self.conv[1], torch.cat([skip_x, self.up(x)], dim=1), t)
 
 
 class _FilteredDown(_TimeConditioned):
@@ -201,7 +213,7 @@ class _FilteredDown(_TimeConditioned):
         self._make_emb(emb_dim, out_channels)
 
     def forward(self, x, t):
-        return self._add_emb(self.conv(ops.custom_downsample(x, self.jinc_filter)), t)
+        return self._blocks_then_emb(self.conv[0], self.conv[1], ops.custom_downsample(x, self.jinc_filter), t)
 
 
 class _FilteredUp(_TimeConditioned):
@@ -217,7 +229,7 @@ class _FilteredUp(_TimeConditioned):
 
     def forward(self, x, skip_x, t):
         # the upsampler writes straight into its half of the concatenated buffer
-        return self._add_emb(self.conv(ops.up2x_cat(skip_x, x, self.sinc_filter)), t)
+        return self._blocks_then_emb(self.conv[0], self.conv[1], ops.up2x_cat(skip_x, x, self.sinc_filter), t)
 
 
 class Down_FF(_FilteredDown):
@@ -241,13 +253,21 @@ class Up_FFF(_FilteredUp):
 
 
 # ---- variant 4 (GroupNorm moved to the 2x grid, between upsample and GELU) ------------------------
-# modules/ddpm_utils.py:145-197, 419-480.  The norm sits between the two resamplers, so the
-# one-kernel fusion does not apply; the block runs as up2x kernel -> nn.GroupNorm -> GELU -> down2x
-# kernel (all with autograd), which keeps the variant available and checkpoint-compatible.
+# modules/ddpm_utils.py:145-197, 419-480.  The norm sits between the two resamplers, so the one-kernel
+# up -> GELU -> down fusion does not apply; what fuses is the second half.  Training: up2x kernel ->
+# nn.GroupNorm -> ONE kernel for GELU + low-pass + decimation (ops.gelu_down2x, with its own adjoint).
+# Inference: the GroupNorm's normalise + affine moves into that kernel as well (statistics from one
+# reduction kernel), so neither norm(u) nor gelu(norm(u)) -- each 4x the activation -- is written.
 class DoubleConv_F4(DoubleConv_F):
     def _act(self, h, norm):
-        h = ops.up2x(h, self.sinc_filter)
-        return ops.down2x(F.gelu(norm(h)), self.jinc_filter)
+        u = ops.up2x(h, self.sinc_filter)
+        if (FUSE_GROUPNORM_INFERENCE and not torch.is_grad_enabled() and u.is_cuda and self.jinc_filter.shape[-1] == 3
+                and u.shape[-1] % 8 == 0 and u.shape[-2] % 2 == 0 and norm.num_groups == 1 and norm.affine):
+            try:
+                return ops.gelu_down2x_affine(u, *_groupnorm1_affine(u, norm), self.jinc_filter)
+            except NotImplementedError:
+                pass
+        return ops.gelu_down2x(norm(u), self.jinc_filter)
 
     def forward(self, x):
         h = self._act(self.conv1(x), self.norm1)

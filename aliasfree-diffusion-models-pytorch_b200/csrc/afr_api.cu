@@ -412,6 +412,82 @@ int afr_filtered_gelu_bwd(const void *x, const void *residual, const void *dy, v
                         stream, true);
 }
 
+int afr_filtered_gelu_affine_bwd(const void *x, const void *residual, const float *scale_dev, const float *shift_dev,
+                                 const void *dy, void *dz, int B, int C, int H, int W, const float *taps_up, int N_up,
+                                 const float *taps_down, int N_down, int dtype, void *stream)
+{
+    if (!scale_dev || !shift_dev) return fail(AFR_ERR_NULL_POINTER, "scale or shift is NULL");
+    return fused_common(x, residual, dy, dz, B, C, H, W, taps_up, N_up, taps_down, N_down, dtype, stream, true,
+                        scale_dev, shift_dev);
+}
+
+int afr_groupnorm1_stats(const void *x, const float *gamma_dev, const float *beta_dev, float eps, const float *add_dev,
+                         float *scale_dev, float *shift_dev, float *mean_dev, float *rstd_dev, int B, int C, int H, int W,
+                         int dtype, void *stream)
+{
+    if (B < 0 || C < 1 || H < 1 || W < 1) return fail(AFR_ERR_BAD_SHAPE, "bad shape");
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if (B == 0) return AFR_OK;
+    if (!x || !gamma_dev || !beta_dev || !scale_dev || !shift_dev) return fail(AFR_ERR_NULL_POINTER, "NULL pointer");
+    const long hw = (long)H * W;
+    if (((long)C * hw) % 4 != 0 || (reinterpret_cast<uintptr_t>(x) % (4 * esz(dtype))) != 0)
+        return fail(AFR_ERR_UNSUPPORTED, "C*H*W must be a multiple of 4 and x aligned to 4 elements");
+    begin_call();
+    g_last_kernel = "groupnorm1_affine_kernel";
+    return cuda_status(groupnorm1_affine(x, gamma_dev, beta_dev, eps, scale_dev, shift_dev, B, C, hw, dtype,
+                                         (cudaStream_t)stream, add_dev, mean_dev, rstd_dev),
+                       "groupnorm1_affine_kernel");
+}
+
+int afr_affine_apply(const void *x, const float *scale_dev, const float *shift_dev, void *y, int B, int C, int H, int W,
+                     int dtype, void *stream)
+{
+    if (B < 0 || C < 1 || H < 1 || W < 1) return fail(AFR_ERR_BAD_SHAPE, "bad shape");
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if (B == 0) return AFR_OK;
+    if (!x || !y || !scale_dev || !shift_dev) return fail(AFR_ERR_NULL_POINTER, "NULL pointer");
+    const long hw = (long)H * W;
+    if (hw % 4 != 0 || (reinterpret_cast<uintptr_t>(x) % (4 * esz(dtype))) != 0 || (reinterpret_cast<uintptr_t>(y) % (4 * esz(dtype))) != 0)
+        return fail(AFR_ERR_UNSUPPORTED, "H*W must be a multiple of 4 and x, y aligned to 4 elements");
+    begin_call();
+    g_last_kernel = "affine_apply_kernel";
+    return cuda_status(affine_apply(x, scale_dev, shift_dev, y, (long)B * C, hw, dtype, (cudaStream_t)stream), "affine_apply_kernel");
+}
+
+int afr_gelu_down2x_fwd(const void *v, const float *scale_dev, const float *shift_dev, void *y, int B, int C, int H,
+                        int W, const float *taps, int N, int dtype, void *stream)
+{
+    if (int rc = check_common(B, C, H, W, taps, N)) return rc;
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if ((scale_dev == nullptr) != (shift_dev == nullptr)) return fail(AFR_ERR_NULL_POINTER, "scale and shift go together");
+    const long planes = (long)B * C;
+    if (planes == 0) return AFR_OK;
+    if (!v || !y) return fail(AFR_ERR_NULL_POINTER, "v or y is NULL");
+    begin_call();
+    if (N != 3 || current_path() == AFR_PATH_GENERIC || !actdown_supported(H, W, v, y, dtype))
+        return fail(AFR_ERR_UNSUPPORTED, "gelu_down2x needs N == 3, even H, W %% 8 == 0 and aligned buffers (N=%d H=%d W=%d)", N, H, W);
+    Taps3 k; set_taps3(k, taps, false);
+    g_last_kernel = "gelu_down3_kernel";
+    return cuda_status(actdown_fwd(v, scale_dev, shift_dev, y, planes, H, W, k, dtype, (cudaStream_t)stream), "gelu_down3_kernel");
+}
+
+int afr_gelu_down2x_bwd(const void *v, const void *dy, void *dv, int B, int C, int H, int W, const float *taps, int N,
+                        int dtype, void *stream)
+{
+    if (int rc = check_common(B, C, H, W, taps, N)) return rc;
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    const long planes = (long)B * C;
+    if (planes == 0) return AFR_OK;
+    if (!v || !dy || !dv) return fail(AFR_ERR_NULL_POINTER, "NULL tensor pointer");
+    begin_call();
+    if (N != 3 || current_path() == AFR_PATH_GENERIC || !actdown_supported(H, W, v, dy, dtype) ||
+        (reinterpret_cast<uintptr_t>(dv) % (8 * esz(dtype))) != 0)
+        return fail(AFR_ERR_UNSUPPORTED, "gelu_down2x adjoint needs N == 3, even H, W %% 8 == 0 and aligned buffers (N=%d H=%d W=%d)", N, H, W);
+    Taps3 k; set_taps3(k, taps, true);
+    g_last_kernel = "gelu_up3_bwd_kernel";
+    return cuda_status(actdown_bwd(v, dy, dv, planes, H, W, k, dtype, (cudaStream_t)stream), "gelu_up3_bwd_kernel");
+}
+
 int afr_rotate_periodic_cubic(const void *x, void *y, int B, int C, int H, int W, double degrees,
                               int dtype, void *stream)
 {

@@ -82,11 +82,21 @@ bool small_down_supported(int H, int W, const void *in, const void *out, long in
 cudaError_t small_down_like(const void *in, void *out, long planes, int C, long in_bstride, int H, int W,
                             const Taps3 &k, int dtype, cudaStream_t s);
 
+// afr_actdown.cu -- variant 4: gelu (+ GroupNorm affine) fused into the N == 3 downsampler, and its adjoint
+bool actdown_supported(int H, int W, const void *v, const void *y, int dtype);
+cudaError_t actdown_fwd(const void *v, const float *scale, const float *shift, void *y, long planes, int H, int W,
+                        const Taps3 &k, int dtype, cudaStream_t s);
+cudaError_t actdown_bwd(const void *v, const void *dy, void *dv, long planes, int H, int W, const Taps3 &kflip, int dtype,
+                        cudaStream_t s);
+
 // afr_rotate.cu
 cudaError_t rotate_periodic_cubic(const float *x, float *y, long planes, int H, int W,
                                   double degrees, cudaStream_t s);
 cudaError_t groupnorm1_affine(const void *x, const float *gamma, const float *beta, float eps, float *scale,
-                              float *shift, long B, int C, long hw, int dtype, cudaStream_t s);
+                              float *shift, long B, int C, long hw, int dtype, cudaStream_t s, const float *add = nullptr,
+                              float *mean_out = nullptr, float *rstd_out = nullptr);
+cudaError_t affine_apply(const void *x, const float *scale, const float *shift, void *y, long planes, long hw, int dtype,
+                         cudaStream_t s);
 cudaError_t ddpm_update(float *x, const float *eps, const float *noise, long n, float ca,
                         float cb, float cc, const float *table_dev, const int *step_dev, cudaStream_t s);
 

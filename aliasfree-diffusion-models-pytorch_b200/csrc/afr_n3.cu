@@ -577,6 +577,8 @@ template <typename T, bool kRes, int HH>
 struct LazyRows {
     const T *xp, *rp;
     int s;
+    float a, b;                                       // x * a + b on load (a = 1, b = 0 without the affine)
+    bool affine;
     __device__ __forceinline__ void load(int row, float (&o)[6]) const
     {
         if (row >= HH) {
@@ -587,6 +589,10 @@ struct LazyRows {
         const T *p = xp + row * HH + 4 * s;
         float4 c4 = ld4(p);
         float nb = (HH == 8) ? ld1(s == 0 ? p + 4 : p - 1) : 0.f;
+        if (affine) {
+            c4.x = fmaf(c4.x, a, b); c4.y = fmaf(c4.y, a, b); c4.z = fmaf(c4.z, a, b); c4.w = fmaf(c4.w, a, b);
+            nb = fmaf(nb, a, b);
+        }
         if (kRes) {
             const T *q = rp + row * HH + 4 * s;
             const float4 q4 = ld4(q);
@@ -640,8 +646,10 @@ fgelu3_plane_kernel(const T *__restrict__ x, const T *__restrict__ res, const T 
             asm volatile("prefetch.global.L1 [%0];" ::"l"(dp + r * HH + 4 * s));
             if (kRes) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + r * HH + 4 * s));
         }
-        const LazyRows<T, kRes, HH> sx{xp, rp, s};
-        const LazyRows<T, false, HH> sd{dp, nullptr, s};
+        float a = 1.f, b = 0.f;
+        if (kAff) { a = __ldg(scale + p); b = __ldg(shift + p); }
+        const LazyRows<T, kRes, HH> sx{xp, rp, s, a, b, kAff};
+        const LazyRows<T, false, HH> sd{dp, nullptr, s, 1.f, 0.f, false};
         strip_begin<kBwd, KT>(sx, sd, 0, S0);
         PlaneSteps<kBwd, KT, HH>::run(sx, sd, out + p * HW + 4 * s, valid, s == 0, K, S0, S1);
     } else {
@@ -1395,10 +1403,10 @@ cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, const float
                        : launch_direct<T, B, R, A, StepK>(x, res, dy, scale, shift, out, planes, H, W, KG, s);      \
     } while (0)
 #define AFR_GO_T(T)                                                                                          \
-    if (bwd) { if (res) { AFR_GO(T, true, true, false); } else { AFR_GO(T, true, false, false); } }          \
+    if (bwd && scale) { if (res) { AFR_GO(T, true, true, true); } else { AFR_GO(T, true, false, true); } }   \
+    else if (bwd) { if (res) { AFR_GO(T, true, true, false); } else { AFR_GO(T, true, false, false); } }     \
     else if (scale) { if (res) { AFR_GO(T, false, true, true); } else { AFR_GO(T, false, false, true); } }   \
     else { if (res) { AFR_GO(T, false, true, false); } else { AFR_GO(T, false, false, false); } }
-    if (bwd && scale) { set_detail("affine fusion is forward-only"); return cudaErrorNotSupported; }
     SymK KS;
     const StepK KG = {kU, kG, kB};
     const bool sym = allow_sym && make_sym(kU, kG, kB, bwd, dtype == AFR_BF16 && AFR_BF16_LOW_FWD, &KS);

@@ -130,7 +130,8 @@ template <typename T>
 __global__ void __launch_bounds__(1024)
 groupnorm1_affine_kernel(const T *__restrict__ x, const float *__restrict__ gamma,
                          const float *__restrict__ beta, float eps, float *__restrict__ scale,
-                         float *__restrict__ shift, int C, long n_per_sample)
+                         float *__restrict__ shift, int C, long n_per_sample, const float *__restrict__ add,
+                         float *__restrict__ mean_out, float *__restrict__ rstd_out)
 {
     __shared__ double red[32];
     const long b = blockIdx.x;
@@ -155,21 +156,61 @@ groupnorm1_affine_kernel(const T *__restrict__ x, const float *__restrict__ gamm
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float sc = __ldg(gamma + c) * rstd;
         scale[b * C + c] = sc;
-        shift[b * C + c] = __ldg(beta + c) - mf * sc;
+        shift[b * C + c] = __ldg(beta + c) - mf * sc + (add ? __ldg(add + b * C + c) : 0.f);
+    }
+    if (threadIdx.x == 0) {                       // for the GroupNorm backward (training)
+        if (mean_out) mean_out[b] = mf;
+        if (rstd_out) rstd_out[b] = rstd;
     }
 }
 
+// y = x * scale[b, c] + shift[b, c]: the normalise + affine (+ broadcast embedding, folded into shift) epilogue
+// of a GroupNorm whose statistics came from the kernel above.  One plane per blockIdx.y row, 128-bit accesses.
+template <typename T>
+__global__ void __launch_bounds__(256)
+affine_apply_kernel(const T *__restrict__ x, const float *__restrict__ scale, const float *__restrict__ shift,
+                    T *__restrict__ y, long planes, int hw4)
+{
+    const long total = planes * hw4;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long p = i / hw4;
+        const float a = __ldg(scale + p), b = __ldg(shift + p);
+        float4 v = ldv4<T>(x + 4 * i);
+        v.x = fmaf(v.x, a, b); v.y = fmaf(v.y, a, b); v.z = fmaf(v.z, a, b); v.w = fmaf(v.w, a, b);
+        st4(y + 4 * i, v);
+    }
+}
+
+cudaError_t affine_apply(const void *x, const float *scale, const float *shift, void *y, long planes, long hw, int dtype,
+                         cudaStream_t s)
+{
+    const int hw4 = (int)(hw / 4);
+    const long total = planes * hw4;
+    long grid = (total + 255) / 256;
+    if (grid < 1) grid = 1;
+    if (grid > 148 * 32) grid = 148 * 32;
+    if (dtype == AFR_F32)
+        affine_apply_kernel<float><<<(unsigned)grid, 256, 0, s>>>((const float *)x, scale, shift, (float *)y, planes, hw4);
+    else
+        affine_apply_kernel<bf16><<<(unsigned)grid, 256, 0, s>>>((const bf16 *)x, scale, shift, (bf16 *)y, planes, hw4);
+    return cudaGetLastError();
+}
+
 cudaError_t groupnorm1_affine(const void *x, const float *gamma, const float *beta, float eps, float *scale,
-                              float *shift, long B, int C, long hw, int dtype, cudaStream_t s)
+                              float *shift, long B, int C, long hw, int dtype, cudaStream_t s, const float *add,
+                              float *mean_out, float *rstd_out)
 {
     if (B > 0x7fffffffL) return cudaErrorInvalidConfiguration;
     const long n = (long)C * hw;
     // few samples: one big CTA per sample (latency); many samples: 256-thread CTAs (occupancy)
     const int threads = (B < 2 * 148 && n >= 8192) ? 1024 : 256;
     if (dtype == AFR_F32)
-        groupnorm1_affine_kernel<float><<<(unsigned)B, threads, 0, s>>>((const float *)x, gamma, beta, eps, scale, shift, C, n);
+        groupnorm1_affine_kernel<float><<<(unsigned)B, threads, 0, s>>>((const float *)x, gamma, beta, eps, scale, shift, C, n,
+                                                                        add, mean_out, rstd_out);
     else
-        groupnorm1_affine_kernel<bf16><<<(unsigned)B, threads, 0, s>>>((const bf16 *)x, gamma, beta, eps, scale, shift, C, n);
+        groupnorm1_affine_kernel<bf16><<<(unsigned)B, threads, 0, s>>>((const bf16 *)x, gamma, beta, eps, scale, shift, C, n,
+                                                                       add, mean_out, rstd_out);
     return cudaGetLastError();
 }
 

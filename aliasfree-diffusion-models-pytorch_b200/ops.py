@@ -269,6 +269,72 @@ def filtered_gelu_affine(x, scale, shift, filt_up, filt_down, residual=None):
     return y
 
 
+def _actdown_ok(v, k):
+    H, W = v.shape[-2:]
+    return k.n == 3 and H % 2 == 0 and W % 8 == 0 and _native.lib().afr_set_path(-1) != _native.PATHS["generic"]
+
+
+class _GeluDown2x(torch.autograd.Function):
+    """down2x(gelu(v)) in one kernel; saves v only and recomputes gelu'(v) in the adjoint kernel."""
+
+    @staticmethod
+    def forward(ctx, v, k):
+        B, C, H, W = v.shape
+        y = torch.empty((B, C, H // 2, W // 2), dtype=v.dtype, device=v.device)
+        with torch.cuda.device(v.device):
+            _check(_native.lib().afr_gelu_down2x_fwd(v.data_ptr(), None, None, y.data_ptr(), B, C, H, W, k.ptr, k.n,
+                                                     _DT[v.dtype], _stream(v)))
+        ctx.k = k
+        ctx.save_for_backward(v)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        (v,) = ctx.saved_tensors
+        B, C, H, W = v.shape
+        dv = torch.empty_like(v)
+        dy = dy.contiguous().to(v.dtype)
+        with torch.cuda.device(v.device):
+            _check(_native.lib().afr_gelu_down2x_bwd(v.data_ptr(), dy.data_ptr(), dv.data_ptr(), B, C, H, W, ctx.k.ptr,
+                                                     ctx.k.n, _DT[v.dtype], _stream(v)))
+        return dv, None
+
+
+def gelu_down2x(v, filt):
+    """``custom_downsample(gelu(v), filt)`` (modules/ddpm_utils.py:172-173, 182-183: the second half of variant
+    4's activation, after the GroupNorm on the 2x grid) in ONE kernel with autograd; gelu(v), a 4x-sized tensor,
+    is never written.  Shapes the fused kernel does not cover run as F.gelu + down2x."""
+    v = _require(v, "v")
+    k = _taps(filt)
+    if _actdown_ok(v, k):
+        return _GeluDown2x.apply(v, k)
+    # the composite keeps gelu(v) in fp32 so that bf16 tensors see ONE rounding, like the fused kernel
+    return _Down2x.apply(torch.nn.functional.gelu(v.float()), k).to(v.dtype)
+
+
+def gelu_down2x_affine(v, scale, shift, filt):
+    """Inference-only: ``custom_downsample(gelu(v * scale[:, :, None, None] + shift[:, :, None, None]), filt)`` --
+    GroupNorm's normalise + affine (statistics from ``groupnorm1_affine``), GELU, low-pass and decimation in one
+    kernel (modules/ddpm_utils.py:171-173).  Raises ``NotImplementedError`` for unsupported shapes."""
+    v = _require(v, "v")
+    k = _taps(filt)
+    if torch.is_grad_enabled() and (v.requires_grad or scale.requires_grad or shift.requires_grad):
+        raise RuntimeError("afr: gelu_down2x_affine is forward-only (use GroupNorm + gelu_down2x to train)")
+    if not _actdown_ok(v, k):
+        raise NotImplementedError("afr: gelu_down2x_affine needs N == 3, even H and W % 8 == 0")
+    B, C, H, W = v.shape
+    scale = scale.detach().to(torch.float32).contiguous()
+    shift = shift.detach().to(torch.float32).contiguous()
+    if tuple(scale.shape) != (B, C) or tuple(shift.shape) != (B, C) or not scale.is_cuda or not shift.is_cuda:
+        raise ValueError("afr: scale and shift must be CUDA tensors of shape [B, C]")
+    y = torch.empty((B, C, H // 2, W // 2), dtype=v.dtype, device=v.device)
+    with torch.cuda.device(v.device):
+        _check(_native.lib().afr_gelu_down2x_fwd(v.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B, C, H, W,
+                                                 k.ptr, k.n, _DT[v.dtype], _stream(v)))
+    return y
+
+
 def groupnorm1_affine(x, weight, bias, eps):
     """Statistics of ``GroupNorm(1, C)`` as the [B, C] (scale, shift) pair that
     ``filtered_gelu_affine`` consumes, in ONE kernel.  Forward only."""
@@ -283,6 +349,122 @@ def groupnorm1_affine(x, weight, bias, eps):
                                                    scale.data_ptr(), shift.data_ptr(), B, C, H, W,
                                                    _DT[x.dtype], _stream(x)))
     return scale, shift
+
+
+# ---- GroupNorm(1, C) folded into its neighbours, with autograd -------------------
+def _gn_stats(h, weight, bias, eps, add=None):
+    """One reduction kernel: per-(sample, channel) scale / shift of GroupNorm(1, C) (+ `add` [B, C] folded into
+    shift) and the per-sample mean / rstd the backward needs."""
+    B, C, H, W = h.shape
+    w = weight.detach().to(torch.float32).contiguous()
+    b = bias.detach().to(torch.float32).contiguous()
+    scale = torch.empty((B, C), dtype=torch.float32, device=h.device)
+    shift = torch.empty((B, C), dtype=torch.float32, device=h.device)
+    mean = torch.empty((B, 1), dtype=torch.float32, device=h.device)
+    rstd = torch.empty((B, 1), dtype=torch.float32, device=h.device)
+    a = None if add is None else add.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(h.device):
+        _check(_native.lib().afr_groupnorm1_stats(h.data_ptr(), w.data_ptr(), b.data_ptr(), float(eps),
+                                                  None if a is None else a.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                  mean.data_ptr(), rstd.data_ptr(), B, C, H, W, _DT[h.dtype], _stream(h)))
+    return scale, shift, mean, rstd
+
+
+def _gn_backward(dz, h, mean, rstd, weight):
+    """GroupNorm(1, C) backward (dz = gradient of the normalised + affine output): ATen's own kernels."""
+    B, C, H, W = h.shape
+    return torch.ops.aten.native_group_norm_backward(dz, h, mean, rstd, weight, B, C, H * W, 1, [True, True, True])
+
+
+class _NormFilteredGelu(torch.autograd.Function):
+    """filtered_gelu(GroupNorm(1, C)(h) + residual): statistics in one reduction kernel, normalise + affine inside
+    the fused activation kernel's load -- the normalised tensor is never written.  Backward: the adjoint kernel
+    recomputes it the same way and yields the gradient of the normalised tensor; ATen finishes the GroupNorm."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, eps, res, ku, kd):
+        B, C, H, W = h.shape
+        scale, shift, mean, rstd = _gn_stats(h, weight, bias, eps)
+        y = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            _check(_native.lib().afr_filtered_gelu_affine_fwd(
+                h.data_ptr(), None if res is None else res.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
+                B, C, H, W, ku.ptr, ku.n, kd.ptr, kd.n, _DT[h.dtype], _stream(h)))
+        ctx.ku, ctx.kd, ctx.has_res = ku, kd, res is not None
+        ctx.save_for_backward(h, weight, scale, shift, mean, rstd, *(() if res is None else (res,)))
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        h, weight, scale, shift, mean, rstd = ctx.saved_tensors[:6]
+        res = ctx.saved_tensors[6] if ctx.has_res else None
+        B, C, H, W = h.shape
+        dz = torch.empty_like(h)
+        dy = dy.contiguous().to(h.dtype)
+        with torch.cuda.device(h.device):
+            _check(_native.lib().afr_filtered_gelu_affine_bwd(
+                h.data_ptr(), None if res is None else res.data_ptr(), scale.data_ptr(), shift.data_ptr(), dy.data_ptr(),
+                dz.data_ptr(), B, C, H, W, ctx.ku.ptr, ctx.ku.n, ctx.kd.ptr, ctx.kd.n, _DT[h.dtype], _stream(h)))
+        dh, dw, db = _gn_backward(dz, h, mean, rstd, weight)
+        return dh, dw, db, None, (dz if ctx.has_res else None), None, None
+
+
+class _NormAddEmb(torch.autograd.Function):
+    """GroupNorm(1, C)(h) + emb[:, :, None, None] as statistics kernel + ONE apply pass (emb folded into the shift)."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, eps, emb):
+        B, C, H, W = h.shape
+        scale, shift, mean, rstd = _gn_stats(h, weight, bias, eps, add=emb)
+        y = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            _check(_native.lib().afr_affine_apply(h.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B, C, H, W,
+                                                  _DT[h.dtype], _stream(h)))
+        ctx.save_for_backward(h, weight, mean, rstd)
+        ctx.emb_dtype = emb.dtype
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        h, weight, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        dh, dw, db = _gn_backward(dy, h, mean, rstd, weight)
+        return dh, dw, db, None, dy.sum(dim=(2, 3)).to(ctx.emb_dtype)
+
+
+def norm_fusable(h, norm, n_up=3, n_down=3):
+    """Can GroupNorm `norm` applied to `h` be folded into the kernels that follow it?  (N == 3 kernels, rows of
+    4-element groups, GroupNorm(1, C) with affine; with autograd only in fp32 -- ATen's backward takes our fp32
+    statistics.)"""
+    if not (isinstance(h, torch.Tensor) and h.is_cuda and h.dim() == 4 and h.dtype in _DT):
+        return False
+    if norm.num_groups != 1 or not norm.affine or n_up != 3 or n_down != 3 or h.shape[-1] % 4 != 0:
+        return False
+    if torch.is_grad_enabled() and (h.requires_grad or norm.weight.requires_grad):
+        return h.dtype == torch.float32 and norm.weight.dtype == torch.float32 and not torch.is_autocast_enabled()
+    return True
+
+
+def norm_filtered_gelu(h, norm, filt_up, filt_down, residual=None):
+    """``filtered_gelu(norm(h) + residual)`` for a ``GroupNorm(1, C)`` module `norm` (modules/ddpm_utils.py:122-125,
+    127-131) without writing the normalised tensor; differentiable.  Check ``norm_fusable`` first."""
+    h = _require(h, "h")
+    if residual is not None:
+        residual = _require(residual, "residual")
+        if residual.dtype != h.dtype or residual.shape != h.shape:
+            raise ValueError("afr: residual must match h in shape and dtype")
+    return _NormFilteredGelu.apply(h, norm.weight, norm.bias, norm.eps, residual, _taps(filt_up), _taps(filt_down))
+
+
+def norm_add_emb(h, norm, emb):
+    """``norm(h) + emb[:, :, None, None]`` (the tail of every Down / Up stage, modules/ddpm_utils.py:385-387,
+    415-417: GroupNorm, ``.repeat`` of the time embedding, add) in one statistics kernel + one apply pass."""
+    h = _require(h, "h")
+    if emb.dim() != 2 or tuple(emb.shape) != tuple(h.shape[:2]):
+        raise ValueError("afr: emb must be [B, C]")
+    return _NormAddEmb.apply(h, norm.weight, norm.bias, norm.eps, emb)
 
 
 def custom_upsample(x, sinc_filter, factor=2):

@@ -392,13 +392,13 @@ def ddpm_v3(afr, ws, rank, global_batch, steps, warmup, schedule):
     use_graph = all_ok(graph_ok, ws)
     if not use_graph and graph_ok:
         mode = "eager (another rank could not capture)"
-    l0 = afr.launch_count()
     full_s, res = _wall_max(lambda: parallel.sharded_sample(diff, net, global_batch, 3, seed=0, gather=(global_batch % ws == 0),
                                                             cuda_graph=use_graph), ws)
     x_u8, result_u8 = res
     n_steps = schedule - 1
     out.update({"samples_per_sec": global_batch / full_s, "full_run_s": full_s, "reverse_steps": n_steps, "mode": mode,
-                "ms_per_reverse_step": 1e3 * full_s / n_steps, "afr_launches_full_run": int(afr.launch_count() - l0),
+                "ms_per_reverse_step": 1e3 * full_s / n_steps,
+                "afr_kernels_full_run": int(launches) * n_steps,      # per captured step x graph replays (replays bypass the C-ABI counter)
                 "snapshots": int(result_u8.shape[0] // x_u8.shape[0]), "gathered_images": int(x_u8.shape[0]),
                 "output_dtype": str(x_u8.dtype).replace("torch.", ""),
                 "full": bool(schedule == 1000)})

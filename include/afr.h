@@ -116,8 +116,8 @@ int afr_filtered_gelu_fwd(const void *x, const void *residual, void *y,
 /* Forward with the normalise + affine step of the preceding GroupNorm(1, C) folded into the load
  * (modules/ddpm_utils.py:122-125 and 127-131):  y = filtered_gelu(x * scale[b,c] + shift[b,c] (+ residual)).
  * scale_dev / shift_dev: DEVICE float32 [B*C] (gamma_c * rstd_b and beta_c - mean_b * gamma_c * rstd_b).
- * The conv zero padding applies to the normalised tensor, exactly as upstream.  Inference path:
- * there is no adjoint; N_up == N_down == 3 and W % 4 == 0 required (AFR_ERR_UNSUPPORTED otherwise). */
+ * The conv zero padding applies to the normalised tensor, exactly as upstream.
+ * N_up == N_down == 3 and W % 4 == 0 required (AFR_ERR_UNSUPPORTED otherwise); adjoint: ..._affine_bwd. */
 int afr_filtered_gelu_affine_fwd(const void *x, const void *residual, const float *scale_dev,
                                  const float *shift_dev, void *y, int B, int C, int H, int W,
                                  const float *taps_up, int N_up, const float *taps_down, int N_down,
@@ -131,12 +131,48 @@ int afr_groupnorm1_affine(const void *x, const float *gamma_dev, const float *be
                           float *scale_dev, float *shift_dev, int B, int C, int H, int W, int dtype,
                           void *stream);
 
+/* afr_groupnorm1_affine plus what training and the block epilogue need: `add_dev` (may be NULL) is a DEVICE fp32
+ * [B*C] term folded into shift -- the time-embedding broadcast `x + emb[:, :, None, None]` that follows the last
+ * GroupNorm of every Down / Up stage (modules/ddpm_utils.py:386, 416); mean_dev / rstd_dev (may be NULL) receive
+ * the per-sample statistics the GroupNorm backward needs. */
+int afr_groupnorm1_stats(const void *x, const float *gamma_dev, const float *beta_dev, float eps,
+                         const float *add_dev, float *scale_dev, float *shift_dev, float *mean_dev,
+                         float *rstd_dev, int B, int C, int H, int W, int dtype, void *stream);
+
+/* y = x * scale[b,c] + shift[b,c]: normalise + affine (+ the folded embedding) of a GroupNorm whose statistics came
+ * from afr_groupnorm1_stats, as one pass (the reference runs GroupNorm, `.repeat` of the embedding and an add:
+ * modules/ddpm_utils.py:385-387).  H*W must be a multiple of 4. */
+int afr_affine_apply(const void *x, const float *scale_dev, const float *shift_dev, void *y,
+                     int B, int C, int H, int W, int dtype, void *stream);
+
+/* adjoint of afr_filtered_gelu_affine_fwd with respect to z = x * scale + shift (+ residual): recomputes z and u
+ * from x, reads dy, writes dz.  The caller finishes with the GroupNorm backward (dz -> dx, dgamma, dbeta), which
+ * needs reductions over the whole sample and stays outside this kernel.  Same restrictions as the forward. */
+int afr_filtered_gelu_affine_bwd(const void *x, const void *residual, const float *scale_dev,
+                                 const float *shift_dev, const void *dy, void *dz, int B, int C, int H, int W,
+                                 const float *taps_up, int N_up, const float *taps_down, int N_down,
+                                 int dtype, void *stream);
+
 /* adjoint of the above wrt (x + residual): recomputes u from x, reads dy, writes dx
  * (d/dx and d/dresidual are the same tensor).  No saved 4x intermediates. */
 int afr_filtered_gelu_bwd(const void *x, const void *residual, const void *dy, void *dx,
                           int B, int C, int H, int W,
                           const float *taps_up, int N_up, const float *taps_down, int N_down,
                           int dtype, void *stream);
+
+/* Variant 4 (DoubleConv_F4, modules/ddpm_utils.py:145-197): GroupNorm sits on the 2x grid between
+ * custom_upsample and the GELU, so only the second half fuses:
+ *     y = custom_downsample(gelu(v * scale[b,c] + shift[b,c]), down)        v [B,C,H,W] = the 2x grid, y [B,C,H/2,W/2]
+ * (lines :171-173 / :181-183; scale_dev / shift_dev as for afr_filtered_gelu_affine_fwd, or both NULL for
+ * y = custom_downsample(gelu(v)) when the caller has already normalised v).  Neither norm(u) nor gelu(norm(u))
+ * -- each 4x the block's activation -- is written.  N == 3, H even, W % 8 == 0 (AFR_ERR_UNSUPPORTED otherwise). */
+int afr_gelu_down2x_fwd(const void *v, const float *scale_dev, const float *shift_dev, void *y,
+                        int B, int C, int H, int W, const float *taps, int N, int dtype, void *stream);
+
+/* adjoint of y = custom_downsample(gelu(v)) (the form without affine, which is what training uses):
+ * dv = gelu'(v) * custom_downsample^T(dy).  v, dv [B,C,H,W]; dy [B,C,H/2,W/2]. */
+int afr_gelu_down2x_bwd(const void *v, const void *dy, void *dv, int B, int C, int H, int W,
+                        const float *taps, int N, int dtype, void *stream);
 
 /* Diffusion.rotate_2d_matrix(matrix, degrees)          modules/ddpm_models.py:421-429
  * = scipy.ndimage.rotate(axes=(2,3), reshape=False, order=3, mode='grid-wrap'):

@@ -166,18 +166,22 @@ def test_groupnorm_fusion_inference_matches_reference(afr):
     outputs must still match the reference fixtures, and equal the unfused path."""
     from aliasfree_b200 import blocks
     g = golden("blocks.npz")
-    for tag in ("DoubleConv_F.plain", "DoubleConv_F.mid", "DoubleConv_F.res", "Down_FFF", "Up_FFF"):
+    for tag in ("DoubleConv_F.plain", "DoubleConv_F.mid", "DoubleConv_F.res", "Down_FFF", "Up_FFF", "DoubleConv_F4.res",
+                "Down_F4", "Up_F4"):
         mod = fill_params_(_block_cases(afr)[tag](), salt=tag).cuda().eval()
         ins = [dev(g[f"{tag}.in{n}"]) for n in range(2) if f"{tag}.in{n}" in g.files]
         args = ins + ([dev(g["t"])] if tag.startswith(("Down", "Up")) else [])
         with torch.no_grad():
             fused = mod(*args)
-            assert afr.last_kernel() in ("fgelu3_tma_kernel<sym>", "fgelu3_direct_kernel<sym>")
-            blocks.FUSE_GROUPNORM_INFERENCE = False
+            # variant 4: GELU + down with the norm folded in; Configs C / D: the whole up -> GELU -> down
+            # (stages end with the embedding folded into the last GroupNorm's apply pass)
+            assert afr.last_kernel() in (("gelu_down3_kernel",) if "F4" in tag else
+                                         ("fgelu3_tma_kernel<sym>", "fgelu3_direct_kernel<sym>", "affine_apply_kernel"))
+            blocks.FUSE_GROUPNORM_INFERENCE = blocks.FUSE_GROUPNORM = False
             try:
                 unfused = mod(*args)
             finally:
-                blocks.FUSE_GROUPNORM_INFERENCE = True
+                blocks.FUSE_GROUPNORM_INFERENCE = blocks.FUSE_GROUPNORM = True
         assert relmax(host(fused), g[f"{tag}.y"]) <= BLOCK_TOL, tag
         assert relmax(host(fused), host(unfused)) <= 2e-5, tag
     gu = golden("unet.npz")
@@ -185,6 +189,36 @@ def test_groupnorm_fusion_inference_matches_reference(afr):
     with torch.no_grad():
         y = net(dev(gu["v3_s16_c3.x"]), dev(gu["v3_s16_c3.t"]))
     assert relmax(host(y), gu["v3_s16_c3.y"]) <= UNET_TOL
+
+
+@pytest.mark.parametrize("tag", ["DoubleConv_F.plain", "DoubleConv_F.res", "Down_FFF", "Up_FFF", "Down_F", "Up_F"])
+def test_groupnorm_fusion_training_matches_unfused(afr, tag):
+    """With autograd the GroupNorm fold (statistics kernel + normalise/affine inside the activation kernel, its
+    adjoint kernel + ATen's GroupNorm backward) and the embedding add folded into the last GroupNorm must give
+    the same outputs, input gradients and parameter gradients as nn.GroupNorm run separately -- and both match
+    the reference fixtures."""
+    from aliasfree_b200 import blocks
+    g = golden("blocks.npz")
+    res = {}
+    for fused in (True, False):
+        mod = fill_params_(_block_cases(afr)[tag](), salt=tag).cuda()
+        ins = [dev(g[f"{tag}.in{n}"], grad=True) for n in range(2) if f"{tag}.in{n}" in g.files]
+        blocks.FUSE_GROUPNORM = fused
+        try:
+            l0 = afr.launch_count()
+            y = mod(*ins, dev(g["t"])) if tag.startswith(("Down", "Up")) else mod(*ins)
+            grads = torch.autograd.grad(y, ins + list(mod.parameters()), dev(g[f"{tag}.dy"]))
+            torch.cuda.synchronize()
+            res[fused] = (y.detach(), grads, afr.launch_count() - l0)
+        finally:
+            blocks.FUSE_GROUPNORM = True
+    assert res[True][2] > res[False][2]                      # the statistics / apply kernels are ours now
+    assert relmax(host(res[True][0]), g[f"{tag}.y"]) <= BLOCK_TOL
+    assert relmax(host(res[True][0]), host(res[False][0])) <= 2e-5
+    for n in range(len(ins)):
+        assert relmax(host(res[True][1][n]), g[f"{tag}.din{n}"]) <= BLOCK_TOL
+    for a_, b_ in zip(res[True][1], res[False][1]):
+        assert relmax(host(a_), host(b_)) <= 5e-5
 
 
 def test_groupnorm1_affine_kernel(afr):

@@ -344,15 +344,17 @@ def test_headline_tensors_sampled_against_oracle(afr, oracle, shape, dtype):
     assert relmax(got, oracle.up2x(host(x.reshape(B * C, H, W)[uidx]), kn)) <= tol
 
 
-@pytest.mark.parametrize("path", ["tma", "tma_general", "direct", "direct_general"])
-@pytest.mark.parametrize("shape", [(2, 4, 32, 32), (1, 2, 64, 64), (2, 2, 16, 24), (1, 3, 24, 136), (1, 2, 40, 264),
-                                   (3, 2, 8, 8), (5, 3, 4, 4)])
+_BF16_FAMILY_SHAPES = [(2, 4, 32, 32), (1, 2, 64, 64), (2, 2, 16, 24), (1, 3, 24, 136), (1, 2, 40, 264), (3, 2, 8, 8),
+                       (5, 3, 4, 4)]
+
+
+@pytest.mark.parametrize("shape,path", [(s_, p_) for s_ in _BF16_FAMILY_SHAPES
+                                        for p_ in ("tma", "tma_general", "direct", "direct_general")
+                                        if not (p_.startswith("tma") and s_[-1] < 8)])     # 4-wide bf16 rows are 8 bytes: no TMA
 def test_oracle_bf16_every_n3_family_fwd_and_adjoint(afr, oracle, shape, path):
     """bf16 storage through each N == 3 kernel family explicitly (TMA ring with symmetric and with general
     taps, direct / whole-plane kernels), forward, adjoint and the fused residual, against the fp32 oracle
     evaluated on the bf16-rounded inputs."""
-    if path.startswith("tma") and (shape[-1] < 8 or shape[-2] < 2):
-        pytest.skip("TMA cannot describe 4-wide bf16 rows (8 bytes)")
     rng = np.random.default_rng(sum(shape))
     k = oracle.lowpass_taps(np.pi / 2, 3, 2.0)
     xb = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
@@ -463,6 +465,52 @@ def test_up2x_cat_writes_into_the_concat_buffer(afr, oracle, shape, cs, dtype):
         gb = dev(rng.standard_normal(tuple(big.shape)).astype(np.float32), dtype)
         (gxb,) = torch.autograd.grad(big, xb, gb)
         assert relmax(host(gxb), oracle.up2x_bwd(host(gb[:, 4:]), k)) <= tol
+
+
+def _gelu64(v):
+    from scipy.special import erf
+    v = np.asarray(v, np.float64)
+    return 0.5 * v * (1.0 + erf(v / np.sqrt(2.0)))
+
+
+def _gelu_grad64(v):
+    from scipy.special import erf
+    v = np.asarray(v, np.float64)
+    return 0.5 * (1.0 + erf(v / np.sqrt(2.0))) + v * np.exp(-0.5 * v * v) / np.sqrt(2.0 * np.pi)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 3, 8, 8), (1, 2, 16, 24), (3, 1, 64, 64), (1, 1, 2, 8), (2, 2, 20, 136), (1, 5, 32, 16),
+                                   (2, 1, 6, 7)])
+def test_gelu_down2x_variant4(afr, oracle, shape, dtype):
+    """Second half of variant 4's activation (modules/ddpm_utils.py:171-173): GELU + low-pass + decimation in one
+    kernel, with and without the GroupNorm affine folded in, and the adjoint kernel; checked against
+    oracle.down2x(gelu(.)) with the exact erf GELU in double."""
+    B, C, H, W = shape
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    rng = np.random.default_rng(H + 7 * W)
+    k = (oracle.lowpass_taps(np.pi / 2, 3, 2.0) + 0.03 * rng.standard_normal((3, 3))).astype(np.float32)
+    v = dev(rng.standard_normal(shape).astype(np.float32), dtype)
+    v32 = host(v)
+    fused = H % 2 == 0 and W % 8 == 0
+    vt = v.clone().requires_grad_(True)
+    y = afr.gelu_down2x(vt, k)
+    if fused:
+        assert afr.last_kernel() == "gelu_down3_kernel"
+    assert relmax(host(y), oracle.down2x(_gelu64(v32).astype(np.float32), k)) <= tol
+    dy = dev(rng.standard_normal(tuple(y.shape)).astype(np.float32), dtype)
+    (dv,) = torch.autograd.grad(y, vt, dy)
+    want = _gelu_grad64(v32) * oracle.down2x_bwd(host(dy), k, H, W)
+    assert relmax(host(dv), want) <= tol
+    if fused:
+        scale = dev(1.0 + 0.3 * rng.standard_normal((B, C)).astype(np.float32))
+        shift = dev(0.5 * rng.standard_normal((B, C)).astype(np.float32))
+        with torch.no_grad():
+            ya = afr.ops.gelu_down2x_affine(v, scale, shift, k)
+        z = v32.astype(np.float64) * host(scale)[:, :, None, None] + host(shift)[:, :, None, None]
+        assert relmax(host(ya), oracle.down2x(_gelu64(z).astype(np.float32), k)) <= (2e-5 if dtype == torch.float32 else tol)
+        with pytest.raises(RuntimeError):
+            afr.ops.gelu_down2x_affine(vt, scale, shift, k)
 
 
 def test_kernel_selection(afr):
