@@ -62,7 +62,10 @@ def lst(path, out, title):
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
             f.write(f"| {100 * v[1] / tot:.1f}% | {v[1]:.1f} | {v[0]} | `{k}` |\n")
         ours = sum(v[1] for k, v in agg.items() if "afr::" in k)
-        f.write(f"\nshare of afr:: kernels: {100 * ours / tot:.1f}%\n")
+        f.write(f"\nshare of afr:: kernels: {100 * ours / tot:.1f}% of the time, {sum(v[0] for k, v in agg.items() if 'afr::' in k)} launches\n")
+        f.write("\nMost-launched kernels:\n\n| launches | us | kernel |\n|---|---|---|\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]:
+            f.write(f"| {v[0]} | {v[1]:.1f} | `{k}` |\n")
     print(open(out).read())
 
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Run one op on one shape a few times (for ncu / quick timing).
 usage: python tools/run_case.py OP B C H W [dtype=f32] [path=auto] [reps=5]
-OP in: fgelu_fwd fgelu_bwd fgelu_fwd_res up down up_bwd down_bwd"""
+OP in: fgelu_fwd fgelu_bwd fgelu_fwd_res up down up_bwd down_bwd gelu_down gelu_down_bwd"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -21,7 +21,9 @@ small = torch.randn(B, C, H // 2, W // 2, device="cuda").to(dt) if op == "down_b
 fn = {"fgelu_fwd": lambda: afr.ops._fgelu_fwd(x, None, k, k), "fgelu_bwd": lambda: afr.ops._fgelu_bwd(x, None, dy, k, k),
       "fgelu_fwd_res": lambda: afr.ops._fgelu_fwd(x, r, k, k), "up": lambda: afr.ops._up_fwd(x, k, dt),
       "down": lambda: afr.ops._down_fwd(x, k), "up_bwd": lambda: afr.ops._up_bwd(big, k, H, W),
-      "down_bwd": lambda: afr.ops._down_bwd(small, k, H, W)}[op]
+      "down_bwd": lambda: afr.ops._down_bwd(small, k, H, W),
+      "gelu_down": lambda: afr.ops._GeluDown2x.apply(x, k),
+      "gelu_down_bwd": lambda: afr.ops._GeluDown2x.apply(x.requires_grad_(True), k).backward(torch.ones(B, C, H // 2, W // 2, device="cuda").to(dt))}[op]
 flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
 ts = []
 for _ in range(reps):
