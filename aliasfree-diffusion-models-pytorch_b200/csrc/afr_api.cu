@@ -195,8 +195,8 @@ int afr_up2x_bwd(const void *du, void *dx, int B, int C, int H, int W, const flo
     }
     if (N == 3 && path != AFR_PATH_GENERIC && n3_down_supported(2 * H, 2 * W, du, dx, du_dtype)) {
         Taps3 k; set_taps3(k, taps, true);
-        g_last_kernel = "down3_kernel";
-        return cuda_status(n3_down_like(du, dx, planes, 2 * H, 2 * W, k, du_dtype, s), "down3_kernel");
+        g_last_kernel = flat_down_wanted(2 * H, 2 * W, du_dtype) ? "down3_flat_kernel" : "down3_kernel";
+        return cuda_status(n3_down_like(du, dx, planes, 2 * H, 2 * W, k, du_dtype, s), g_last_kernel);
     }
     TapsG t; set_taps(t, taps, N, true);
     if (path == AFR_PATH_AUTO && stripn_resample_supported(N) && n3_down_supported(2 * H, 2 * W, du, dx, du_dtype)) {
@@ -255,9 +255,9 @@ int afr_up2x_bwd_strided(const void *du, void *dx, int B, int C, int H, int W, i
     }
     if (!strip_ok)
         return fail(AFR_ERR_UNSUPPORTED, "strided up2x adjoint needs W %% 4 == 0 and 16-byte aligned slice base / batch stride (H=%d W=%d)", H, W);
-    g_last_kernel = "down3_kernel";
+    g_last_kernel = flat_down_wanted(2 * H, 2 * W, dtype) ? "down3_flat_kernel" : "down3_kernel";
     return cuda_status(n3_down_like(du, dx, planes, 2 * H, 2 * W, k, dtype, (cudaStream_t)stream, C, (long)du_batch_stride),
-                       "down3_kernel");
+                       g_last_kernel);
 }
 
 int afr_down2x_fwd(const void *v, void *y, int B, int C, int H, int W, const float *taps, int N,
@@ -280,8 +280,8 @@ int afr_down2x_fwd(const void *v, void *y, int B, int C, int H, int W, const flo
     }
     if (N == 3 && path != AFR_PATH_GENERIC && n3_down_supported(H, W, v, y, dtype)) {
         Taps3 k; set_taps3(k, taps, false);
-        g_last_kernel = "down3_kernel";
-        return cuda_status(n3_down_like(v, y, planes, H, W, k, dtype, s), "down3_kernel");
+        g_last_kernel = flat_down_wanted(H, W, dtype) ? "down3_flat_kernel" : "down3_kernel";
+        return cuda_status(n3_down_like(v, y, planes, H, W, k, dtype, s), g_last_kernel);
     }
     TapsG t; set_taps(t, taps, N, false);
     if (path == AFR_PATH_AUTO && stripn_resample_supported(N) && n3_down_supported(H, W, v, y, dtype)) {

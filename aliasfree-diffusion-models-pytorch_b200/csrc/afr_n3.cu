@@ -1464,6 +1464,7 @@ cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, c
                          int dtype, cudaStream_t s, int C, long in_bstride)
 {
     if (planes > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    if (flat_down_wanted(H, W, dtype)) return flat_down_like(in, out, planes, C, in_bstride, H, W, k, dtype, s);
     const int Ho = (H + 1) / 2, Wo = W / 2;
     // bf16: 8 outputs per thread when the row width and the bases allow 128-bit vectors both ways
     const bool wide = dtype == AFR_BF16 && (Wo % 8) == 0 && aligned_to(in, 16) && aligned_to(out, 16);

@@ -259,6 +259,78 @@ down3_warp_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, in
     store2<T>(out + (long)p * (HO * WO) + i * WO + 2 * s, o[0], o[1]);
 }
 
+// ---- down-like without a row loop ("flat"): one thread per (plane, output row, V output columns) -----------
+// The strip kernel of afr_n3.cu walks down the rows with the odd row carried, which exposes one memory latency per
+// output row; short planes are latency-bound there (ncu: long_scoreboard).  Here every thread issues ALL its loads up front -- three input rows, 2V columns as 128-bit
+// loads plus the left halo -- and the grid is (planes x rows x strips) threads, so the loads in flight are bounded
+// by occupancy alone.  Row 2i-1 is read by two threads (L1 / L2 hit): 1.5x the load instructions, the same DRAM bytes.
+template <typename T, int V, int ROWS>
+__global__ void __launch_bounds__(256)
+down3_flat_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, int W, int Ho, int Wo, int strips,
+                  int C, long in_bstride, const __grid_constant__ Taps3 k)
+{
+    // 32-bit index arithmetic (the launcher guarantees planes * strips * rgroups < 2^32): with 64-bit divisions the
+    // index bookkeeping was ~2/3 of this kernel's instructions (ncu: 267 instructions per thread, XU pipe 17 %)
+    const unsigned rgroups = (unsigned)(Ho + ROWS - 1) / ROWS;     // ROWS consecutive output rows per thread
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned per_plane = (unsigned)strips * rgroups;
+    const unsigned pu = idx / per_plane, rem = idx - pu * per_plane;
+    if (pu >= (unsigned long)planes) return;
+    const unsigned rg = rem / (unsigned)strips;
+    const int s = (int)(rem - rg * (unsigned)strips);
+    const int i0 = (int)rg * ROWS;
+    const long p = pu;
+    const int j = V * s;
+    const T *plane = in + strided_base((unsigned)p, C, in_bstride, (long)H * W);
+    const bool has_l = (j > 0);
+    float v[2 * ROWS + 1][2 * V + 1];
+#pragma unroll
+    for (int r = 0; r < 2 * ROWS + 1; ++r) {
+        const int row = 2 * i0 - 1 + r;
+        if (row < 0 || row >= H) {
+#pragma unroll
+            for (int c = 0; c < 2 * V + 1; ++c) v[r][c] = 0.f;
+        } else {
+            const T *q = plane + (long)row * W + 2 * j;
+#pragma unroll
+            for (int h = 0; h < V / 4; ++h) {
+                float w[8];
+                ld8(q + 8 * h, w);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[r][8 * h + c + 1] = w[c];
+            }
+            v[r][0] = has_l ? ld1(q - 1) : 0.f;
+        }
+    }
+    T *dst = out + p * (long)Ho * Wo + (long)i0 * Wo + j;
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+        if (i0 + rr >= Ho) break;
+        float o[V];
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            float acc = k.k[0][0] * v[2 * rr][2 * q];
+            acc = fmaf(k.k[0][1], v[2 * rr][2 * q + 1], acc);
+            acc = fmaf(k.k[0][2], v[2 * rr][2 * q + 2], acc);
+            acc = fmaf(k.k[1][0], v[2 * rr + 1][2 * q], acc);
+            acc = fmaf(k.k[1][1], v[2 * rr + 1][2 * q + 1], acc);
+            acc = fmaf(k.k[1][2], v[2 * rr + 1][2 * q + 2], acc);
+            acc = fmaf(k.k[2][0], v[2 * rr + 2][2 * q], acc);
+            acc = fmaf(k.k[2][1], v[2 * rr + 2][2 * q + 1], acc);
+            acc = fmaf(k.k[2][2], v[2 * rr + 2][2 * q + 2], acc);
+            o[q] = acc;
+        }
+        if (V == 8) {
+            float o8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o8[q] = o[q % V];
+            st8(dst + (long)rr * Wo, o8);
+        } else {
+            st4(dst + (long)rr * Wo, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+}
+
 int group_planes(int plane_floats, long planes)
 {
     // ~24 KB of staged planes per CTA, a multiple of 8 planes (keeps every CTA's output block 16-byte aligned),
@@ -389,6 +461,51 @@ cudaError_t small_down_like(const void *in, void *out, long planes, int C, long 
         down3_group_kernel<float><<<(unsigned)grid, 256, smem, s>>>((const float *)in, (float *)out, planes, C, in_bstride, H, W, pg, k);
     else
         down3_group_kernel<bf16><<<(unsigned)grid, 256, smem, s>>>((const bf16 *)in, (bf16 *)out, planes, C, in_bstride, H, W, pg, k);
+    return cudaGetLastError();
+}
+
+}  // namespace afr
+
+namespace afr {
+
+// AFR_DOWN_FLAT: 0 = never, 1 = fp32 only (default), 2 = fp32 and bf16.
+// Measured (B200, L2 left clean before each repetition): fp32 0.86 -> 1.00 on 32x32 planes and 0.98 -> 1.06 of the
+// copy-measured HBM peak on 64x64 (a read-dominated kernel can exceed a copy's rate); bf16 gains nothing
+// (0.48 / 0.51 -> 0.52 / 0.57, the strip kernel's wide variant reaches 0.64 on 64x64), so bf16 keeps the strip kernel.
+static int down_flat_mode()
+{
+    static const int v = []() { const char *e = getenv("AFR_DOWN_FLAT"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
+// same shape / alignment conditions as the strip kernel (n3_down_supported): W % 8 == 0, 8-element aligned input
+bool flat_down_wanted(int H, int W, int dtype)
+{
+    (void)H; (void)W;
+    const int m = down_flat_mode();
+    return m == 2 || (m == 1 && dtype == AFR_F32);
+}
+
+cudaError_t flat_down_like(const void *in, void *out, long planes, int C, long in_bstride, int H, int W, const Taps3 &k,
+                           int dtype, cudaStream_t s)
+{
+    const int Ho = (H + 1) / 2, Wo = W / 2;
+    static const bool want_wide = []() { const char *e = getenv("AFR_DOWN_FLAT_WIDE"); return e && atoi(e) != 0; }();
+    static const int want_rows = []() { const char *e = getenv("AFR_DOWN_FLAT_ROWS"); return e ? atoi(e) : 0; }();
+    const bool wide = want_wide && dtype == AFR_BF16 && (Wo % 8) == 0 && (reinterpret_cast<uintptr_t>(in) % 16) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) % 16) == 0;
+    const int V = wide ? 8 : 4;
+    const int strips = Wo / V;
+    int rows = want_rows > 0 ? want_rows : 1;
+    if (rows != 1 && rows != 2) rows = 2;
+    const long total = planes * (long)strips * ((Ho + rows - 1) / rows);
+    const long grid = (total + 255) / 256;
+    if (total >= 0xffffff00L || planes > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+#define AFR_FLAT(T, VV, RR) down3_flat_kernel<T, VV, RR><<<(unsigned)grid, 256, 0, s>>>((const T *)in, (T *)out, planes, H, W, Ho, Wo, strips, C, in_bstride, k)
+    if (dtype == AFR_F32) { if (rows == 2) AFR_FLAT(float, 4, 2); else AFR_FLAT(float, 4, 1); }
+    else if (wide) { if (rows == 2) AFR_FLAT(bf16, 8, 2); else AFR_FLAT(bf16, 8, 1); }
+    else { if (rows == 2) AFR_FLAT(bf16, 4, 2); else AFR_FLAT(bf16, 4, 1); }
+#undef AFR_FLAT
     return cudaGetLastError();
 }
 

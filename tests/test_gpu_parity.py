@@ -391,10 +391,12 @@ def _up_kernel_name(h, w):
     return "up3_warp_kernel" if (h, w) in WARP_UP else "up3_kernel"
 
 
-def _down_kernel_name(h, w):
+def _down_kernel_name(h, w, dtype=torch.float32):
     if (h, w) in WARP_DOWN:
         return "down3_warp_kernel"
-    return "down3_kernel" if w % 8 == 0 else "down3_group_kernel"
+    if w % 8 == 0:                       # loop-free form for fp32, row-walking strips for bf16
+        return "down3_flat_kernel" if dtype == torch.float32 else "down3_kernel"
+    return "down3_group_kernel"
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
@@ -415,10 +417,10 @@ def test_small_plane_kernels(afr, oracle, shape, dtype):
     assert relmax(host(u), oracle.up2x(x32, k)) <= tol
     du = dev(rng.standard_normal(tuple(u.shape)).astype(np.float32), dtype)
     gx = afr.ops._up_bwd(du, kt, H, W)
-    assert afr.last_kernel() == _down_kernel_name(2 * H, 2 * W)
+    assert afr.last_kernel() == _down_kernel_name(2 * H, 2 * W, dtype)
     assert relmax(host(gx), oracle.up2x_bwd(host(du), k)) <= tol
     d = afr.ops._down_fwd(x, kt)
-    assert afr.last_kernel() == _down_kernel_name(H, W)
+    assert afr.last_kernel() == _down_kernel_name(H, W, dtype)
     assert tuple(d.shape) == (B, C, (H + 1) // 2, W // 2)
     assert relmax(host(d), oracle.down2x(x32, k)) <= tol
     dd = dev(rng.standard_normal(tuple(d.shape)).astype(np.float32), dtype)

@@ -18,6 +18,9 @@ except Exception:
     PEAK = 6555.2
 k = afr.Taps(afr.circularLowpassKernel(np.pi / 2, 3, 2))
 flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+flush_r = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
+CLEAN = os.environ.get("AB_CLEAN_FLUSH", "1") != "0"     # read pass after the write pass: L2 is left full of CLEAN lines
+sink = torch.zeros((), device="cuda")
 
 
 def tm(fn, reps=7):
@@ -25,6 +28,8 @@ def tm(fn, reps=7):
     ts = []
     for _ in range(reps):
         flush.zero_()
+        if CLEAN:
+            sink.add_(flush_r.sum())
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
