@@ -160,8 +160,8 @@ int afr_up2x_fwd(const void *x, void *u, int B, int C, int H, int W, const float
     }
     if (N == 3 && path != AFR_PATH_GENERIC && n3_up_supported(H, W, x, u, in_dtype, out_dtype)) {
         Taps3 k; set_taps3(k, taps, false);
-        g_last_kernel = "up3_kernel";
-        return cuda_status(n3_up_like(x, u, planes, H, W, k, in_dtype, out_dtype, s), "up3_kernel");
+        g_last_kernel = flat_up_wanted(H, W, in_dtype, out_dtype) ? "up3_flat_kernel" : "up3_kernel";
+        return cuda_status(n3_up_like(x, u, planes, H, W, k, in_dtype, out_dtype, s), g_last_kernel);
     }
     TapsG t; set_taps(t, taps, N, false);
     if (path == AFR_PATH_AUTO && stripn_resample_supported(N) && n3_up_supported(H, W, x, u, in_dtype, out_dtype)) {
@@ -229,9 +229,9 @@ int afr_up2x_fwd_strided(const void *x, void *u, int B, int C, int H, int W, int
     }
     if (!strip_ok)
         return fail(AFR_ERR_UNSUPPORTED, "strided up2x needs W %% 4 == 0, 32-byte aligned slice base and batch stride (H=%d W=%d)", H, W);
-    g_last_kernel = "up3_kernel";
+    g_last_kernel = flat_up_wanted(H, W, in_dtype, out_dtype) ? "up3_flat_kernel" : "up3_kernel";
     return cuda_status(n3_up_like(x, u, planes, H, W, k, in_dtype, out_dtype, (cudaStream_t)stream, C, (long)out_batch_stride),
-                       "up3_kernel");
+                       g_last_kernel);
 }
 
 int afr_up2x_bwd_strided(const void *du, void *dx, int B, int C, int H, int W, int64_t du_batch_stride,
@@ -316,8 +316,8 @@ int afr_down2x_bwd(const void *dy, void *dv, int B, int C, int H, int W, const f
     if (N == 3 && path != AFR_PATH_GENERIC && (H % 2) == 0 && (W % 2) == 0 &&
         n3_up_supported(Ho, Wo, dy, dv, dtype, dtype)) {
         Taps3 k; set_taps3(k, taps, true);
-        g_last_kernel = "up3_kernel";
-        return cuda_status(n3_up_like(dy, dv, planes, Ho, Wo, k, dtype, dtype, s), "up3_kernel");
+        g_last_kernel = flat_up_wanted(Ho, Wo, dtype, dtype) ? "up3_flat_kernel" : "up3_kernel";
+        return cuda_status(n3_up_like(dy, dv, planes, Ho, Wo, k, dtype, dtype, s), g_last_kernel);
     }
     TapsG t; set_taps(t, taps, N, true);
     if (path == AFR_PATH_AUTO && stripn_resample_supported(N) && (H % 2) == 0 && (W % 2) == 0 &&

@@ -87,6 +87,10 @@ bool flat_down_wanted(int H, int W, int dtype);
 cudaError_t flat_down_like(const void *in, void *out, long planes, int C, long in_bstride, int H, int W, const Taps3 &k,
                            int dtype, cudaStream_t s);
 
+bool flat_up_wanted(int H, int W, int in_dtype, int out_dtype);
+cudaError_t flat_up_like(const void *in, void *out, long planes, int C, long out_bstride, int H, int W, const Taps3 &k,
+                         int in_dtype, int out_dtype, cudaStream_t s);
+
 // afr_actdown.cu -- variant 4: gelu (+ GroupNorm affine) fused into the N == 3 downsampler, and its adjoint
 bool actdown_supported(int H, int W, const void *v, const void *y, int dtype);
 cudaError_t actdown_fwd(const void *v, const float *scale, const float *shift, void *y, long planes, int H, int W,

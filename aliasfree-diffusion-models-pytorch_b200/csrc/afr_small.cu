@@ -331,6 +331,46 @@ down3_flat_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, in
     }
 }
 
+// ---- up-like without a row loop: one thread per (plane, input row, 4 input columns) -> 2 x 8 outputs --------
+// Same idea as down3_flat_kernel: both input rows (i and i+1; the latter is re-read by the thread below, an L1 / L2
+// hit) are requested up front and the grid supplies the parallelism.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+up3_flat_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int H, int W, int strips, int C,
+                long out_bstride, const __grid_constant__ Taps3 k)
+{
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned per_plane = (unsigned)strips * (unsigned)H;
+    const unsigned pu = idx / per_plane, rem = idx - pu * per_plane;
+    if (pu >= (unsigned long)planes) return;
+    const unsigned i = rem / (unsigned)strips;
+    const int s = (int)(rem - i * (unsigned)strips), j = 4 * s;
+    const TI *src = in + (long)pu * H * W + (long)i * W + j;
+    const bool has_r = (j + 4 < W), has_b = ((int)i + 1 < H);
+    const float4 ca = ld4(src);
+    float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ra = 0.f, rb = 0.f;
+    if (has_b) cb = ld4(src + W);
+    if (has_r) ra = ld1(src + 4);
+    if (has_r && has_b) rb = ld1(src + W + 4);
+    const float xa[5] = {ca.x, ca.y, ca.z, ca.w, ra}, xb[5] = {cb.x, cb.y, cb.z, cb.w, rb};
+    float e[8], o[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        e[2 * c] = k.k[1][1] * xa[c];
+        e[2 * c + 1] = fmaf(k.k[1][2], xa[c + 1], k.k[1][0] * xa[c]);
+        o[2 * c] = fmaf(k.k[2][1], xb[c], k.k[0][1] * xa[c]);
+        float t = k.k[0][0] * xa[c];
+        t = fmaf(k.k[0][2], xa[c + 1], t);
+        t = fmaf(k.k[2][0], xb[c], t);
+        o[2 * c + 1] = fmaf(k.k[2][2], xb[c + 1], t);
+    }
+    const int W2 = 2 * W;
+    TO *dst = out + strided_base(pu, C, out_bstride, 4L * H * W) + (long)(2 * i) * W2 + 2 * j;
+    st8(dst, e);
+    st8(dst + W2, o);
+}
+
 int group_planes(int plane_floats, long planes)
 {
     // ~24 KB of staged planes per CTA, a multiple of 8 planes (keeps every CTA's output block 16-byte aligned),
@@ -484,6 +524,37 @@ bool flat_down_wanted(int H, int W, int dtype)
     (void)H; (void)W;
     const int m = down_flat_mode();
     return m == 2 || (m == 1 && dtype == AFR_F32);
+}
+
+// AFR_UP_FLAT: 0 = never, 1 = fp32 planes up to 32 x 32 (default), 2 = always.  Measured (B200): fp32 16x16 planes
+// 0.79 -> 0.87, 32x32 0.86 -> 0.88, 64x64 0.92 -> 0.88 (the row-walking strips win once a plane is tall enough to
+// amortise their start-up); bf16: -0 .. -4 % everywhere.
+static int up_flat_mode()
+{
+    static const int v = []() { const char *e = getenv("AFR_UP_FLAT"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
+bool flat_up_wanted(int H, int W, int in_dtype, int out_dtype)
+{
+    const int m = up_flat_mode();
+    return m == 2 || (m == 1 && in_dtype == AFR_F32 && out_dtype == AFR_F32 && (long)H * W <= 1024);
+}
+
+cudaError_t flat_up_like(const void *in, void *out, long planes, int C, long out_bstride, int H, int W, const Taps3 &k,
+                         int in_dtype, int out_dtype, cudaStream_t s)
+{
+    const int strips = W / 4;
+    const long total = planes * (long)strips * H;
+    const long grid = (total + 255) / 256;
+    if (total >= 0xffffff00L || planes > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+#define AFR_UF(TI, TO) up3_flat_kernel<TI, TO><<<(unsigned)grid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, H, W, strips, C, out_bstride, k)
+    if (in_dtype == AFR_F32 && out_dtype == AFR_F32) AFR_UF(float, float);
+    else if (in_dtype == AFR_BF16 && out_dtype == AFR_BF16) AFR_UF(bf16, bf16);
+    else if (in_dtype == AFR_BF16 && out_dtype == AFR_F32) AFR_UF(bf16, float);
+    else AFR_UF(float, bf16);
+#undef AFR_UF
+    return cudaGetLastError();
 }
 
 cudaError_t flat_down_like(const void *in, void *out, long planes, int C, long in_bstride, int H, int W, const Taps3 &k,

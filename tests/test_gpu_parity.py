@@ -387,8 +387,10 @@ WARP_UP = {(4, 4), (8, 8), (8, 4), (4, 8), (2, 4), (2, 8), (16, 8), (16, 4)}
 WARP_DOWN = {(4, 4), (8, 8), (16, 16), (8, 4), (4, 8), (16, 8), (8, 16), (2, 4), (32, 4), (16, 4)}
 
 
-def _up_kernel_name(h, w):
-    return "up3_warp_kernel" if (h, w) in WARP_UP else "up3_kernel"
+def _up_kernel_name(h, w, dtype=torch.float32):
+    if (h, w) in WARP_UP:
+        return "up3_warp_kernel"
+    return "up3_flat_kernel" if dtype == torch.float32 and h * w <= 1024 else "up3_kernel"
 
 
 def _down_kernel_name(h, w, dtype=torch.float32):
@@ -413,7 +415,7 @@ def test_small_plane_kernels(afr, oracle, shape, dtype):
     x = dev(rng.standard_normal(shape).astype(np.float32), dtype)
     x32 = host(x)
     u = afr.ops._up_fwd(x, kt, dtype)
-    assert afr.last_kernel() == _up_kernel_name(H, W)
+    assert afr.last_kernel() == _up_kernel_name(H, W, dtype)
     assert relmax(host(u), oracle.up2x(x32, k)) <= tol
     du = dev(rng.standard_normal(tuple(u.shape)).astype(np.float32), dtype)
     gx = afr.ops._up_bwd(du, kt, H, W)
@@ -426,7 +428,7 @@ def test_small_plane_kernels(afr, oracle, shape, dtype):
     dd = dev(rng.standard_normal(tuple(d.shape)).astype(np.float32), dtype)
     gx = afr.ops._down_bwd(dd, kt, H, W)
     if H % 2 == 0:
-        assert afr.last_kernel() == _up_kernel_name(H // 2, W // 2) or W // 2 < 4
+        assert afr.last_kernel() == _up_kernel_name(H // 2, W // 2, dtype) or W // 2 < 4
     assert relmax(host(gx), oracle.down2x_bwd(host(dd), k, H, W)) <= tol
     if dtype == torch.bfloat16:
         assert relmax(host(afr.custom_upsample(x, k)), oracle.up2x(x32, k)) <= FP32_TOL     # bf16 in, fp32 out
@@ -449,7 +451,7 @@ def test_up2x_cat_writes_into_the_concat_buffer(afr, oracle, shape, cs, dtype):
     skip = dev(rng.standard_normal((B, cs, 2 * H, 2 * W)).astype(np.float32), dtype).requires_grad_(True)
     n0 = afr.launch_count()
     out = afr.up2x_cat(skip, x, k)
-    assert afr.launch_count() == n0 + 1 and afr.last_kernel() == _up_kernel_name(H, W)
+    assert afr.launch_count() == n0 + 1 and afr.last_kernel() == _up_kernel_name(H, W, dtype)
     assert tuple(out.shape) == (B, cs + C, 2 * H, 2 * W) and out.is_contiguous()
     assert torch.equal(out[:, :cs], skip)
     assert relmax(host(out[:, cs:]), oracle.up2x(host(x), k)) <= tol
