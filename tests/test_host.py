@@ -68,6 +68,63 @@ def test_c_abi_argument_errors_without_gpu(afr):
     assert L.afr_status_string(6) == b"CUDA error"
 
 
+def test_c_abi_argument_errors_of_the_round2_entry_points(afr):
+    """Strided upsample, variant-4 GELU + down, GroupNorm statistics / apply, affine adjoint: validation before CUDA."""
+    L = afr._native.lib()
+    taps = (ctypes.c_float * 9)(*([1 / 9.0] * 9))
+    taps5 = (ctypes.c_float * 25)(*([1 / 25.0] * 25))
+    p = ctypes.c_void_p(1 << 20)                       # never dereferenced: every call below fails validation first
+    assert L.afr_up2x_fwd_strided(p, p, 2, 3, 4, 4, 10, taps, 3, 0, 0, None) == 1           # batch stride < C*2H*2W
+    assert b"out_batch_stride" in L.afr_last_error()
+    assert L.afr_up2x_fwd_strided(p, p, 2, 3, 4, 4, 4 * 3 * 16, taps5, 5, 0, 0, None) == 7  # N != 3: caller falls back
+    assert L.afr_up2x_fwd_strided(None, None, 0, 3, 4, 4, 4 * 3 * 16, taps, 3, 0, 0, None) == 0
+    assert L.afr_up2x_bwd_strided(p, p, 1, 1, 4, 4, 1, taps, 3, 0, None) == 1
+    assert L.afr_gelu_down2x_fwd(p, None, None, p, 1, 1, 8, 8, taps5, 5, 0, None) == 7      # N != 3
+    assert L.afr_gelu_down2x_fwd(p, None, None, p, 1, 1, 7, 8, taps, 3, 0, None) == 7       # odd H
+    assert L.afr_gelu_down2x_fwd(p, p, None, p, 1, 1, 8, 8, taps, 3, 0, None) == 4          # scale without shift
+    assert L.afr_gelu_down2x_bwd(p, None, p, 1, 1, 8, 8, taps, 3, 0, None) == 4
+    assert L.afr_groupnorm1_stats(p, p, p, 1e-5, None, None, p, None, None, 1, 4, 4, 4, 0, None) == 4
+    assert L.afr_groupnorm1_stats(p, p, p, 1e-5, None, p, p, None, None, 1, 3, 1, 1, 0, None) == 7   # C*H*W % 4
+    assert L.afr_affine_apply(p, p, p, p, 1, 1, 3, 3, 0, None) == 7                          # H*W % 4
+    assert L.afr_affine_apply(p, p, p, p, 0, 1, 4, 4, 0, None) == 0
+    assert L.afr_filtered_gelu_affine_bwd(p, None, None, None, p, p, 1, 1, 8, 8, taps, 3, taps, 3, 0, None) == 4
+    assert L.afr_set_path(-1) == 0 and afr._native.PATHS_AUTO()                               # pure query
+
+
+def test_reference_install_is_byte_identical():
+    """baseline/_ref (what travels to the GPU box) is the unmodified reference: every file's SHA-256 equals the
+    manifest, and equals /root/reference when that checkout is present."""
+    import hashlib
+    import json
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "modules")):
+        pytest.skip("baseline/_ref not installed (run tools/install_ref.py where /root/reference exists)")
+    man = json.load(open(os.path.join(ref, "MANIFEST.json")))["sha256"]
+    assert {"modules/filtrs.py", "modules/ddpm_utils.py", "modules/ddpm_models.py"} <= set(man)
+    for rel, sha in man.items():
+        assert hashlib.sha256(open(os.path.join(ref, rel), "rb").read()).hexdigest() == sha, rel
+        live = os.path.join("/root/reference", rel)
+        if os.path.exists(live):
+            assert open(live, "rb").read() == open(os.path.join(ref, rel), "rb").read(), rel
+    tracked = subprocess.run(["git", "-C", ROOT, "ls-files", "baseline/_ref"], capture_output=True, text=True).stdout
+    assert tracked.strip() == ""                        # never committed
+
+
+def test_groupnorm_fold_is_cuda_only_and_modules_fall_back_cleanly(afr):
+    """The fold is decided per call (ops.norm_fusable): CPU tensors are never fusable, so the blocks reach the plain
+    GroupNorm + filtered_gelu path, which then refuses CPU tensors loudly (no CPU fallback anywhere)."""
+    blk = afr.DoubleConv_F(4, 4, f_settings=FS)
+    h = torch.randn(2, 4, 8, 8)
+    assert not afr.ops.norm_fusable(h, blk.norm1)
+    assert not afr.ops.norm_fusable(h.to(torch.float64), blk.norm1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        blk(h)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        afr.gelu_down2x(h, afr.circularLowpassKernel(np.pi / 2, 3, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        afr.up2x_cat(torch.randn(2, 4, 16, 16), h, afr.circularLowpassKernel(np.pi / 2, 3, 2))
+
+
 def test_no_cpu_fallback(afr):
     k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
     x = torch.randn(1, 2, 8, 8)
