@@ -37,6 +37,17 @@ def _groupnorm1_affine(h, norm):
     return ops.groupnorm1_affine(h, norm.weight, norm.bias, norm.eps)
 
 
+def _cached_taps(module, name):
+    """``ops.Taps`` of the filter attribute `name`, rebuilt only when a user swaps the tensor (the conversion to a
+    pinned-down fp32 host copy costs ~5 us per call otherwise)."""
+    filt = getattr(module, name)
+    cache = module.__dict__.setdefault("_taps_cache", {})
+    hit = cache.get(name)
+    if hit is None or hit[0] is not filt:
+        hit = cache[name] = (filt, ops.Taps(filt))
+    return hit[1]
+
+
 def _conv3(cin, cout):
     return nn.Conv2d(cin, cout, kernel_size=3, padding=1, bias=False)
 
@@ -213,7 +224,7 @@ class _FilteredDown(_TimeConditioned):
         self._make_emb(emb_dim, out_channels)
 
     def forward(self, x, t):
-        return self._blocks_then_emb(self.conv[0], self.conv[1], ops.custom_downsample(x, self.jinc_filter), t)
+        return self._blocks_then_emb(self.conv[0], self.conv[1], ops.custom_downsample(x, _cached_taps(self, "jinc_filter")), t)
 
 
 class _FilteredUp(_TimeConditioned):
@@ -229,7 +240,7 @@ class _FilteredUp(_TimeConditioned):
 
     def forward(self, x, skip_x, t):
         # the upsampler writes straight into its half of the concatenated buffer
-        return self._blocks_then_emb(self.conv[0], self.conv[1], ops.up2x_cat(skip_x, x, self.sinc_filter), t)
+        return self._blocks_then_emb(self.conv[0], self.conv[1], ops.up2x_cat(skip_x, x, _cached_taps(self, "sinc_filter")), t)
 
 
 class Down_FF(_FilteredDown):

@@ -22,8 +22,35 @@ def _check(rc):
         raise RuntimeError("afr: %s: %s" % (L.afr_status_string(rc).decode(), L.afr_last_error().decode()))
 
 
+try:                                           # raw handle of torch's current stream without building a Stream object
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:                         # older torch
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+
+
 def _stream(t):
-    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return ctypes.c_void_p(_raw_stream(t.device.index))
+
+
+class _on_device:
+    """``with torch.cuda.device(t.device)`` that costs nothing when that device is already current (the common
+    case: one process per GPU).  A launch from Python is ~10 us of host time; this and the raw stream handle take
+    ~4 us off it, which is what the eager small-batch UNet feels (63 of our launches per reverse step)."""
+    __slots__ = ("idx", "guard")
+
+    def __init__(self, device):
+        self.idx, self.guard = device.index, None
+
+    def __enter__(self):
+        if torch.cuda.current_device() != self.idx:
+            self.guard = torch.cuda.device(self.idx)
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
 
 
 def _require(x, name="x"):
@@ -66,7 +93,7 @@ def _taps(filt):
 def _up_fwd(x, k, out_dtype):
     B, C, H, W = x.shape
     u = torch.empty((B, C, 2 * H, 2 * W), dtype=out_dtype, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(_native.lib().afr_up2x_fwd(x.data_ptr(), u.data_ptr(), B, C, H, W, k.ptr, k.n,
                                           _DT[x.dtype], _DT[out_dtype], _stream(x)))
     return u
@@ -75,7 +102,7 @@ def _up_fwd(x, k, out_dtype):
 def _up_bwd(du, k, H, W):
     B, C = du.shape[:2]
     dx = torch.empty((B, C, H, W), dtype=du.dtype, device=du.device)
-    with torch.cuda.device(du.device):
+    with _on_device(du.device):
         _check(_native.lib().afr_up2x_bwd(du.data_ptr(), dx.data_ptr(), B, C, H, W, k.ptr, k.n,
                                           _DT[du.dtype], _DT[dx.dtype], _stream(du)))
     return dx
@@ -84,7 +111,7 @@ def _up_bwd(du, k, H, W):
 def _down_fwd(v, k):
     B, C, H, W = v.shape
     y = torch.empty((B, C, (H + 1) // 2, (W + 1) // 2), dtype=v.dtype, device=v.device)
-    with torch.cuda.device(v.device):
+    with _on_device(v.device):
         _check(_native.lib().afr_down2x_fwd(v.data_ptr(), y.data_ptr(), B, C, H, W, k.ptr, k.n,
                                             _DT[v.dtype], _stream(v)))
     return y
@@ -93,7 +120,7 @@ def _down_fwd(v, k):
 def _down_bwd(dy, k, H, W):
     B, C = dy.shape[:2]
     dv = torch.empty((B, C, H, W), dtype=dy.dtype, device=dy.device)
-    with torch.cuda.device(dy.device):
+    with _on_device(dy.device):
         _check(_native.lib().afr_down2x_bwd(dy.data_ptr(), dv.data_ptr(), B, C, H, W, k.ptr, k.n,
                                             _DT[dy.dtype], _stream(dy)))
     return dv
@@ -102,7 +129,7 @@ def _down_bwd(dy, k, H, W):
 def _fgelu_fwd(x, res, ku, kd, out=None):
     B, C, H, W = x.shape
     y = torch.empty_like(x) if out is None else out
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(_native.lib().afr_filtered_gelu_fwd(
             x.data_ptr(), None if res is None else res.data_ptr(), y.data_ptr(), B, C, H, W,
             ku.ptr, ku.n, kd.ptr, kd.n, _DT[x.dtype], _stream(x)))
@@ -112,11 +139,17 @@ def _fgelu_fwd(x, res, ku, kd, out=None):
 def _fgelu_bwd(x, res, dy, ku, kd):
     B, C, H, W = x.shape
     dx = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(_native.lib().afr_filtered_gelu_bwd(
             x.data_ptr(), None if res is None else res.data_ptr(), dy.data_ptr(), dx.data_ptr(),
             B, C, H, W, ku.ptr, ku.n, kd.ptr, kd.n, _DT[x.dtype], _stream(x)))
     return dx
+
+
+def _needs_grad(*tensors):
+    """Autograd bookkeeping (``Function.apply`` costs ~5 us of host time per call) is only paid when a gradient can
+    actually flow: the no_grad sampler calls the raw launchers directly."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
 # ---- autograd -------------------------------------------------------------------------
@@ -173,16 +206,20 @@ class _Up2xCat(torch.autograd.Function):
     channel slice of the concatenated buffer (and its adjoint reading the gradient slice in place)."""
 
     @staticmethod
-    def forward(ctx, skip, x, k):
+    def run(skip, x, k):
         B, C, H, W = x.shape
         Cs = skip.shape[1]
         out = torch.empty((B, Cs + C, 2 * H, 2 * W), dtype=skip.dtype, device=skip.device)
         out[:, :Cs].copy_(skip)
-        with torch.cuda.device(x.device):
+        with _on_device(x.device):
             _check(_native.lib().afr_up2x_fwd_strided(x.data_ptr(), out[:, Cs:].data_ptr(), B, C, H, W, out.stride(0),
                                                       k.ptr, k.n, _DT[x.dtype], _DT[out.dtype], _stream(x)))
-        ctx.k, ctx.shape, ctx.cs, ctx.in_dtype = k, (B, C, H, W), Cs, x.dtype
         return out
+
+    @staticmethod
+    def forward(ctx, skip, x, k):
+        ctx.k, ctx.shape, ctx.cs, ctx.in_dtype = k, tuple(x.shape), skip.shape[1], x.dtype
+        return _Up2xCat.run(skip, x, k)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -190,7 +227,7 @@ class _Up2xCat(torch.autograd.Function):
         B, C, H, W = ctx.shape
         g = g.contiguous()
         dx = torch.empty((B, C, H, W), dtype=g.dtype, device=g.device)
-        with torch.cuda.device(g.device):
+        with _on_device(g.device):
             _check(_native.lib().afr_up2x_bwd_strided(g[:, ctx.cs:].data_ptr(), dx.data_ptr(), B, C, H, W, g.stride(0),
                                                       ctx.k.ptr, ctx.k.n, _DT[g.dtype], _stream(g)))
         return g[:, :ctx.cs], dx.to(ctx.in_dtype), None
@@ -205,8 +242,8 @@ def up2x_cat(skip, x, filt):
     B, C, H, W = x.shape
     if (k.n == 3 and W % 4 == 0 and skip.shape[0] == B and tuple(skip.shape[2:]) == (2 * H, 2 * W)
             and (skip.shape[1] * 4 * H * W * skip.element_size()) % 32 == 0 and _native.PATHS_AUTO()):
-        return _Up2xCat.apply(skip, x, k)
-    return torch.cat([skip, _Up2x.apply(x, k, skip.dtype)], dim=1)
+        return _Up2xCat.apply(skip, x, k) if _needs_grad(skip, x) else _Up2xCat.run(skip, x, k)
+    return torch.cat([skip, up2x(x, k, skip.dtype)], dim=1)
 
 
 def _match_residual(x, residual):
@@ -225,12 +262,15 @@ def _match_residual(x, residual):
 def up2x(x, filt, out_dtype=None):
     """Zero-stuff x2 + depthwise N x N low-pass, 'same' zero padding, no gain."""
     x = _require(x)
+    if not _needs_grad(x):
+        return _up_fwd(x, _taps(filt), out_dtype or x.dtype)
     return _Up2x.apply(x, _taps(filt), out_dtype or x.dtype)
 
 
 def down2x(x, filt):
     """Depthwise N x N low-pass then keep every 2nd row/column; output is contiguous."""
-    return _Down2x.apply(_require(x), _taps(filt))
+    x = _require(x)
+    return _Down2x.apply(x, _taps(filt)) if _needs_grad(x) else _down_fwd(x, _taps(filt))
 
 
 def filtered_gelu(x, filt_up, filt_down, residual=None):
@@ -239,6 +279,8 @@ def filtered_gelu(x, filt_up, filt_down, residual=None):
     x = _require(x)
     if residual is not None:
         x, residual = _match_residual(x, residual)
+    if not _needs_grad(x, residual):
+        return _fgelu_fwd(x, residual, _taps(filt_up), _taps(filt_down))
     return _FilteredGelu.apply(x, residual, _taps(filt_up), _taps(filt_down))
 
 
@@ -262,7 +304,7 @@ def filtered_gelu_affine(x, scale, shift, filt_up, filt_down, residual=None):
     if residual is not None:
         x, residual = _match_residual(x, residual)
     y = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(_native.lib().afr_filtered_gelu_affine_fwd(
             x.data_ptr(), None if residual is None else residual.data_ptr(), scale.data_ptr(), shift.data_ptr(),
             y.data_ptr(), B, C, H, W, ku.ptr, ku.n, kd.ptr, kd.n, _DT[x.dtype], _stream(x)))
@@ -281,7 +323,7 @@ class _GeluDown2x(torch.autograd.Function):
     def forward(ctx, v, k):
         B, C, H, W = v.shape
         y = torch.empty((B, C, H // 2, W // 2), dtype=v.dtype, device=v.device)
-        with torch.cuda.device(v.device):
+        with _on_device(v.device):
             _check(_native.lib().afr_gelu_down2x_fwd(v.data_ptr(), None, None, y.data_ptr(), B, C, H, W, k.ptr, k.n,
                                                      _DT[v.dtype], _stream(v)))
         ctx.k = k
@@ -295,7 +337,7 @@ class _GeluDown2x(torch.autograd.Function):
         B, C, H, W = v.shape
         dv = torch.empty_like(v)
         dy = dy.contiguous().to(v.dtype)
-        with torch.cuda.device(v.device):
+        with _on_device(v.device):
             _check(_native.lib().afr_gelu_down2x_bwd(v.data_ptr(), dy.data_ptr(), dv.data_ptr(), B, C, H, W, ctx.k.ptr,
                                                      ctx.k.n, _DT[v.dtype], _stream(v)))
         return dv, None
@@ -329,7 +371,7 @@ def gelu_down2x_affine(v, scale, shift, filt):
     if tuple(scale.shape) != (B, C) or tuple(shift.shape) != (B, C) or not scale.is_cuda or not shift.is_cuda:
         raise ValueError("afr: scale and shift must be CUDA tensors of shape [B, C]")
     y = torch.empty((B, C, H // 2, W // 2), dtype=v.dtype, device=v.device)
-    with torch.cuda.device(v.device):
+    with _on_device(v.device):
         _check(_native.lib().afr_gelu_down2x_fwd(v.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B, C, H, W,
                                                  k.ptr, k.n, _DT[v.dtype], _stream(v)))
     return y
@@ -344,7 +386,7 @@ def groupnorm1_affine(x, weight, bias, eps):
     b = bias.detach().to(torch.float32).contiguous()
     scale = torch.empty((B, C), dtype=torch.float32, device=x.device)
     shift = torch.empty((B, C), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(_native.lib().afr_groupnorm1_affine(x.data_ptr(), w.data_ptr(), b.data_ptr(), float(eps),
                                                    scale.data_ptr(), shift.data_ptr(), B, C, H, W,
                                                    _DT[x.dtype], _stream(x)))
@@ -363,7 +405,7 @@ def _gn_stats(h, weight, bias, eps, add=None):
     mean = torch.empty((B, 1), dtype=torch.float32, device=h.device)
     rstd = torch.empty((B, 1), dtype=torch.float32, device=h.device)
     a = None if add is None else add.detach().to(torch.float32).contiguous()
-    with torch.cuda.device(h.device):
+    with _on_device(h.device):
         _check(_native.lib().afr_groupnorm1_stats(h.data_ptr(), w.data_ptr(), b.data_ptr(), float(eps),
                                                   None if a is None else a.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                                   mean.data_ptr(), rstd.data_ptr(), B, C, H, W, _DT[h.dtype], _stream(h)))
@@ -382,14 +424,19 @@ class _NormFilteredGelu(torch.autograd.Function):
     recomputes it the same way and yields the gradient of the normalised tensor; ATen finishes the GroupNorm."""
 
     @staticmethod
-    def forward(ctx, h, weight, bias, eps, res, ku, kd):
+    def run(h, weight, bias, eps, res, ku, kd):
         B, C, H, W = h.shape
         scale, shift, mean, rstd = _gn_stats(h, weight, bias, eps)
         y = torch.empty_like(h)
-        with torch.cuda.device(h.device):
+        with _on_device(h.device):
             _check(_native.lib().afr_filtered_gelu_affine_fwd(
                 h.data_ptr(), None if res is None else res.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
                 B, C, H, W, ku.ptr, ku.n, kd.ptr, kd.n, _DT[h.dtype], _stream(h)))
+        return y, scale, shift, mean, rstd
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, eps, res, ku, kd):
+        y, scale, shift, mean, rstd = _NormFilteredGelu.run(h, weight, bias, eps, res, ku, kd)
         ctx.ku, ctx.kd, ctx.has_res = ku, kd, res is not None
         ctx.save_for_backward(h, weight, scale, shift, mean, rstd, *(() if res is None else (res,)))
         return y
@@ -402,7 +449,7 @@ class _NormFilteredGelu(torch.autograd.Function):
         B, C, H, W = h.shape
         dz = torch.empty_like(h)
         dy = dy.contiguous().to(h.dtype)
-        with torch.cuda.device(h.device):
+        with _on_device(h.device):
             _check(_native.lib().afr_filtered_gelu_affine_bwd(
                 h.data_ptr(), None if res is None else res.data_ptr(), scale.data_ptr(), shift.data_ptr(), dy.data_ptr(),
                 dz.data_ptr(), B, C, H, W, ctx.ku.ptr, ctx.ku.n, ctx.kd.ptr, ctx.kd.n, _DT[h.dtype], _stream(h)))
@@ -414,13 +461,18 @@ class _NormAddEmb(torch.autograd.Function):
     """GroupNorm(1, C)(h) + emb[:, :, None, None] as statistics kernel + ONE apply pass (emb folded into the shift)."""
 
     @staticmethod
-    def forward(ctx, h, weight, bias, eps, emb):
+    def run(h, weight, bias, eps, emb):
         B, C, H, W = h.shape
         scale, shift, mean, rstd = _gn_stats(h, weight, bias, eps, add=emb)
         y = torch.empty_like(h)
-        with torch.cuda.device(h.device):
+        with _on_device(h.device):
             _check(_native.lib().afr_affine_apply(h.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B, C, H, W,
                                                   _DT[h.dtype], _stream(h)))
+        return y, mean, rstd
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, eps, emb):
+        y, mean, rstd = _NormAddEmb.run(h, weight, bias, eps, emb)
         ctx.save_for_backward(h, weight, mean, rstd)
         ctx.emb_dtype = emb.dtype
         return y
@@ -455,6 +507,8 @@ def norm_filtered_gelu(h, norm, filt_up, filt_down, residual=None):
         residual = _require(residual, "residual")
         if residual.dtype != h.dtype or residual.shape != h.shape:
             raise ValueError("afr: residual must match h in shape and dtype")
+    if not _needs_grad(h, residual, norm.weight, norm.bias):
+        return _NormFilteredGelu.run(h, norm.weight, norm.bias, norm.eps, residual, _taps(filt_up), _taps(filt_down))[0]
     return _NormFilteredGelu.apply(h, norm.weight, norm.bias, norm.eps, residual, _taps(filt_up), _taps(filt_down))
 
 
@@ -464,6 +518,8 @@ def norm_add_emb(h, norm, emb):
     h = _require(h, "h")
     if emb.dim() != 2 or tuple(emb.shape) != tuple(h.shape[:2]):
         raise ValueError("afr: emb must be [B, C]")
+    if not _needs_grad(h, emb, norm.weight, norm.bias):
+        return _NormAddEmb.run(h, norm.weight, norm.bias, norm.eps, emb)[0]
     return _NormAddEmb.apply(h, norm.weight, norm.bias, norm.eps, emb)
 
 
@@ -490,7 +546,7 @@ def rotate(x, degrees):
         raise TypeError("afr: rotate needs float32")
     B, C, H, W = x.shape
     y = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(_native.lib().afr_rotate_periodic_cubic(x.data_ptr(), y.data_ptr(), B, C, H, W,
                                                        float(degrees), 0, _stream(x)))
     return y
@@ -501,7 +557,7 @@ def ddpm_update_(x, eps, noise, ca, cb, cc):
     for t in (x, eps) + (() if noise is None else (noise,)):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise RuntimeError("afr: ddpm_update_ needs contiguous float32 CUDA tensors")
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(_native.lib().afr_ddpm_update(x.data_ptr(), eps.data_ptr(),
                                              None if noise is None else noise.data_ptr(),
                                              x.numel(), float(ca), float(cb), float(cc), _stream(x)))
@@ -516,7 +572,7 @@ def ddpm_update_table_(x, eps, noise, table, step):
             raise RuntimeError("afr: ddpm_update_table_ needs contiguous float32 CUDA tensors")
     if not (step.is_cuda and step.dtype == torch.int32):
         raise RuntimeError("afr: step must be an int32 CUDA tensor")
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(_native.lib().afr_ddpm_update_table(x.data_ptr(), eps.data_ptr(),
                                                    None if noise is None else noise.data_ptr(),
                                                    x.numel(), table.data_ptr(), step.data_ptr(), _stream(x)))
