@@ -264,34 +264,47 @@ down3_warp_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, in
 // output row; short planes are latency-bound there (ncu: long_scoreboard).  Here every thread issues ALL its loads up front -- three input rows, 2V columns as 128-bit
 // loads plus the left halo -- and the grid is (planes x rows x strips) threads, so the loads in flight are bounded
 // by occupancy alone.  Row 2i-1 is read by two threads (L1 / L2 hit): 1.5x the load instructions, the same DRAM bytes.
-template <typename T, int V, int ROWS>
+template <typename T, int V, int ROWS, bool kPow2>
 __global__ void __launch_bounds__(256)
 down3_flat_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, int H, int W, int Ho, int Wo, int strips,
-                  int C, long in_bstride, const __grid_constant__ Taps3 k)
+                  int lg_strips, int lg_per_plane, int C, long in_bstride, const __grid_constant__ Taps3 k)
 {
-    // 32-bit index arithmetic (the launcher guarantees planes * strips * rgroups < 2^32): with 64-bit divisions the
-    // index bookkeeping was ~2/3 of this kernel's instructions (ncu: 267 instructions per thread, XU pipe 17 %)
+    // 32-bit index arithmetic (the launcher guarantees planes * strips * rgroups < 2^32); with power-of-two strip and
+    // row-group counts (every power-of-two plane) the thread -> (plane, row group, strip) map is two shifts.  The first
+    // version of this kernel spent 2/3 of its instructions on 64-bit index and address arithmetic (ncu: 267
+    // instructions per thread for 36 FMAs), which is what a bf16 tensor -- half the bytes per element -- ran into.
     const unsigned rgroups = (unsigned)(Ho + ROWS - 1) / ROWS;     // ROWS consecutive output rows per thread
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned per_plane = (unsigned)strips * rgroups;
-    const unsigned pu = idx / per_plane, rem = idx - pu * per_plane;
+    unsigned pu, rg;
+    int s;
+    if (kPow2) {
+        pu = idx >> lg_per_plane;
+        const unsigned rem = idx & ((1u << lg_per_plane) - 1u);
+        rg = rem >> lg_strips;
+        s = (int)(rem & ((1u << lg_strips) - 1u));
+    } else {
+        const unsigned per_plane = (unsigned)strips * rgroups;
+        pu = idx / per_plane;
+        const unsigned rem = idx - pu * per_plane;
+        rg = rem / (unsigned)strips;
+        s = (int)(rem - rg * (unsigned)strips);
+    }
     if (pu >= (unsigned long)planes) return;
-    const unsigned rg = rem / (unsigned)strips;
-    const int s = (int)(rem - rg * (unsigned)strips);
     const int i0 = (int)rg * ROWS;
     const long p = pu;
     const int j = V * s;
-    const T *plane = in + strided_base((unsigned)p, C, in_bstride, (long)H * W);
+    const T *plane = in + strided_base(pu, C, in_bstride, (long)H * W);
     const bool has_l = (j > 0);
+    const int off0 = (2 * i0 - 1) * W + 2 * j;                     // a plane has < 2^30 elements: int offsets
     float v[2 * ROWS + 1][2 * V + 1];
 #pragma unroll
     for (int r = 0; r < 2 * ROWS + 1; ++r) {
         const int row = 2 * i0 - 1 + r;
-        if (row < 0 || row >= H) {
+        if ((unsigned)row >= (unsigned)H) {
 #pragma unroll
             for (int c = 0; c < 2 * V + 1; ++c) v[r][c] = 0.f;
         } else {
-            const T *q = plane + (long)row * W + 2 * j;
+            const T *q = plane + (off0 + r * W);
 #pragma unroll
             for (int h = 0; h < V / 4; ++h) {
                 float w[8];
@@ -508,10 +521,10 @@ cudaError_t small_down_like(const void *in, void *out, long planes, int C, long 
 
 namespace afr {
 
-// AFR_DOWN_FLAT: 0 = never, 1 = fp32 only (default), 2 = fp32 and bf16.
+// AFR_DOWN_FLAT: 0 = never, 1 = fp32 always, bf16 on planes up to 32 x 32 (default), 2 = always.
 // Measured (B200, L2 left clean before each repetition): fp32 0.86 -> 1.00 on 32x32 planes and 0.98 -> 1.06 of the
-// copy-measured HBM peak on 64x64 (a read-dominated kernel can exceed a copy's rate); bf16 gains nothing
-// (0.48 / 0.51 -> 0.52 / 0.57, the strip kernel's wide variant reaches 0.64 on 64x64), so bf16 keeps the strip kernel.
+// copy-measured HBM peak on 64x64 (a read-dominated kernel can exceed a copy's rate); bf16 0.52 -> 0.57 on 32x32 but
+// 0.69 -> 0.61-0.65 on 64x64, where the strip kernel's 8-output variant amortises its conversions better.
 static int down_flat_mode()
 {
     static const int v = []() { const char *e = getenv("AFR_DOWN_FLAT"); return e ? atoi(e) : 1; }();
@@ -521,9 +534,8 @@ static int down_flat_mode()
 // same shape / alignment conditions as the strip kernel (n3_down_supported): W % 8 == 0, 8-element aligned input
 bool flat_down_wanted(int H, int W, int dtype)
 {
-    (void)H; (void)W;
     const int m = down_flat_mode();
-    return m == 2 || (m == 1 && dtype == AFR_F32);
+    return m == 2 || (m == 1 && (dtype == AFR_F32 || (long)H * W <= 1024));
 }
 
 // AFR_UP_FLAT: 0 = never, 1 = fp32 planes up to 32 x 32 (default), 2 = always.  Measured (B200): fp32 16x16 planes
@@ -572,10 +584,16 @@ cudaError_t flat_down_like(const void *in, void *out, long planes, int C, long i
     const long total = planes * (long)strips * ((Ho + rows - 1) / rows);
     const long grid = (total + 255) / 256;
     if (total >= 0xffffff00L || planes > 0x7fffffffL) return cudaErrorInvalidConfiguration;
-#define AFR_FLAT(T, VV, RR) down3_flat_kernel<T, VV, RR><<<(unsigned)grid, 256, 0, s>>>((const T *)in, (T *)out, planes, H, W, Ho, Wo, strips, C, in_bstride, k)
+    const int rgroups = (Ho + rows - 1) / rows;
+    auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+    const bool pow2 = (strips & (strips - 1)) == 0 && (rgroups & (rgroups - 1)) == 0;
+    const int lgs = lg2(strips), lgp = lg2(strips * rgroups);
+#define AFR_FLAT2(T, VV, RR, PP) down3_flat_kernel<T, VV, RR, PP><<<(unsigned)grid, 256, 0, s>>>((const T *)in, (T *)out, planes, H, W, Ho, Wo, strips, lgs, lgp, C, in_bstride, k)
+#define AFR_FLAT(T, VV, RR) do { if (pow2) AFR_FLAT2(T, VV, RR, true); else AFR_FLAT2(T, VV, RR, false); } while (0)
     if (dtype == AFR_F32) { if (rows == 2) AFR_FLAT(float, 4, 2); else AFR_FLAT(float, 4, 1); }
     else if (wide) { if (rows == 2) AFR_FLAT(bf16, 8, 2); else AFR_FLAT(bf16, 8, 1); }
     else { if (rows == 2) AFR_FLAT(bf16, 4, 2); else AFR_FLAT(bf16, 4, 1); }
+#undef AFR_FLAT2
 #undef AFR_FLAT
     return cudaGetLastError();
 }

@@ -396,8 +396,8 @@ def _up_kernel_name(h, w, dtype=torch.float32):
 def _down_kernel_name(h, w, dtype=torch.float32):
     if (h, w) in WARP_DOWN:
         return "down3_warp_kernel"
-    if w % 8 == 0:                       # loop-free form for fp32, row-walking strips for bf16
-        return "down3_flat_kernel" if dtype == torch.float32 else "down3_kernel"
+    if w % 8 == 0:                       # loop-free form; bf16 keeps the row-walking strips above 32 x 32
+        return "down3_flat_kernel" if dtype == torch.float32 or h * w <= 1024 else "down3_kernel"
     return "down3_group_kernel"
 
 
