@@ -1312,6 +1312,15 @@ static bool pick_tile(long planes, int H, int W, int dtype, int nin, int *thread
                     if (resident > 32) resident = 32;
                     c.nsegs = 1;
                     while (2 * ctas * c.nsegs < 5 * 148 * resident && H / (c.nsegs * 2) >= 2 * c.R && c.nsegs < 16) c.nsegs *= 2;
+                    // kernels that stage two or three tensors hold fewer CTAs per SM, which makes the rule above stop
+                    // early; tall planes still gain from the CTA count a one-input launch would get as long as a
+                    // segment keeps >= 64 rows (one dry step per segment): [16,64,256,256] adjoint 0.56 -> 0.60
+                    if (nin > 1) {
+                        long res1 = (long)(220 * 1024) / ((long)c.tile_bytes * 2);
+                        if (res1 > 65536 / (100 * t)) res1 = 65536 / (100 * t);
+                        if (res1 > 32) res1 = 32;
+                        while (2 * ctas * c.nsegs < 5 * 148 * res1 && H / (c.nsegs * 2) >= 64 && c.nsegs < 16) c.nsegs *= 2;
+                    }
                     if (env_nsegs() > 0) c.nsegs = env_nsegs();   // tuning runs
                     c.Hs = ((H + c.nsegs - 1) / c.nsegs + c.R - 1) / c.R * c.R;
                     c.nsegs = (H + c.Hs - 1) / c.Hs;
