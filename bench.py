@@ -593,6 +593,8 @@ def ddp_grad_check(afr, ws, rank, global_batch=64):
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
         torch.manual_seed(0)
+        shards_n = ws if ws > 1 else 2
+        global_batch = max(shards_n, global_batch // shards_n * shards_n)   # equal shards: mean of shard means == global mean
         net = afr.UNet(c_in=3, c_out=3, image_size=32, f_settings=FS, variant=3).cuda().train()
         diff = afr.Diffusion(noise_steps=1000, img_size=32, device="cuda")
         ddp = parallel.FlatGradAllReduce(net)                  # broadcasts rank 0's parameters
