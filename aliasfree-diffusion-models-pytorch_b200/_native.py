@@ -74,6 +74,9 @@ def _declare(L):
     L.afr_filtered_gelu_affine_bwd.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
     L.afr_groupnorm1_stats.argtypes = [vp, vp, vp, cf, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     L.afr_affine_apply.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    L.afr_filtered_gelu_nhwc_fwd.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
+    L.afr_filtered_gelu_nhwc_bwd.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
+    L.afr_affine_apply_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     L.afr_filtered_gelu_bwd.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
     L.afr_gelu_down2x_fwd.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, ci, vp]
     L.afr_gelu_down2x_bwd.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, ci, ci, vp]
@@ -83,7 +86,8 @@ def _declare(L):
     for n in ("afr_up2x_fwd", "afr_up2x_bwd", "afr_down2x_fwd", "afr_down2x_bwd", "afr_up2x_fwd_strided", "afr_up2x_bwd_strided",
               "afr_filtered_gelu_fwd", "afr_filtered_gelu_bwd", "afr_filtered_gelu_affine_fwd", "afr_groupnorm1_affine",
               "afr_rotate_periodic_cubic", "afr_ddpm_update", "afr_ddpm_update_table", "afr_gelu_down2x_fwd",
-              "afr_gelu_down2x_bwd", "afr_filtered_gelu_affine_bwd", "afr_groupnorm1_stats", "afr_affine_apply"):
+              "afr_gelu_down2x_bwd", "afr_filtered_gelu_affine_bwd", "afr_groupnorm1_stats", "afr_affine_apply",
+              "afr_filtered_gelu_nhwc_fwd", "afr_filtered_gelu_nhwc_bwd", "afr_affine_apply_nhwc"):
         getattr(L, n).restype = ci
     return L
 
@@ -93,7 +97,8 @@ EXPORTS = ("afr_version", "afr_last_error", "afr_status_string", "afr_set_path",
            "afr_down2x_fwd", "afr_down2x_bwd",
            "afr_filtered_gelu_fwd", "afr_filtered_gelu_bwd", "afr_filtered_gelu_affine_fwd", "afr_groupnorm1_affine",
            "afr_rotate_periodic_cubic", "afr_ddpm_update", "afr_ddpm_update_table", "afr_gelu_down2x_fwd",
-           "afr_gelu_down2x_bwd", "afr_filtered_gelu_affine_bwd", "afr_groupnorm1_stats", "afr_affine_apply")
+           "afr_gelu_down2x_bwd", "afr_filtered_gelu_affine_bwd", "afr_groupnorm1_stats", "afr_affine_apply",
+           "afr_filtered_gelu_nhwc_fwd", "afr_filtered_gelu_nhwc_bwd", "afr_affine_apply_nhwc")
 
 
 def lib():

@@ -421,6 +421,66 @@ int afr_filtered_gelu_affine_bwd(const void *x, const void *residual, const floa
                         scale_dev, shift_dev);
 }
 
+static int fused_nhwc(const void *x, const void *residual, const float *scale, const float *shift, const void *dy,
+                      void *out, int B, int C, int H, int W, const float *taps_up, int N_up, const float *taps_down,
+                      int N_down, int dtype, void *stream, bool bwd)
+{
+    if (int rc = check_common(B, C, H, W, taps_up, N_up)) return rc;
+    if (int rc = check_common(B, C, H, W, taps_down, N_down)) return rc;
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if ((scale == nullptr) != (shift == nullptr)) return fail(AFR_ERR_NULL_POINTER, "scale and shift go together");
+    if ((long)B * C == 0) return AFR_OK;
+    if (!x || !out || (bwd && !dy)) return fail(AFR_ERR_NULL_POINTER, "NULL tensor pointer");
+    begin_call();
+    const void *ptrs[4] = {x, residual, bwd ? dy : nullptr, out};
+    if (N_up != 3 || N_down != 3 || current_path() == AFR_PATH_GENERIC || !nhwc_fgelu_supported(C, H, W, ptrs, 4))
+        return fail(AFR_ERR_UNSUPPORTED, "channels-last fused kernel needs 3x3 filters, C %% 32 == 0, W %% 4 == 0, H >= 2 and "
+                                         "16-byte aligned buffers (C=%d H=%d W=%d)", C, H, W);
+    Taps3 kU, kG, kB;
+    set_taps3(kU, taps_up, false);
+    if (bwd)
+        for (int i = 0; i < 9; ++i) kU.k[i / 3][i % 3] *= AFR_KAPPA;
+    set_taps3(kG, taps_down, true);
+    set_taps3(kB, bwd ? taps_up : taps_down, bwd);
+    const cudaError_t e = nhwc_fgelu(x, residual, dy, scale, shift, out, B, C, H, W, kU, kG, kB, bwd, dtype, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported)
+        return fail(AFR_ERR_UNSUPPORTED, "channels-last fused kernel needs D4-symmetric taps (non-negative up taps in the forward)");
+    g_last_kernel = "fgelu3_nhwc_kernel<sym>";
+    return cuda_status(e, "fgelu3_nhwc_kernel");
+}
+
+int afr_filtered_gelu_nhwc_fwd(const void *x, const void *residual, const float *scale_dev, const float *shift_dev, void *y,
+                               int B, int C, int H, int W, const float *taps_up, int N_up, const float *taps_down,
+                               int N_down, int dtype, void *stream)
+{
+    return fused_nhwc(x, residual, scale_dev, shift_dev, nullptr, y, B, C, H, W, taps_up, N_up, taps_down, N_down, dtype,
+                      stream, false);
+}
+
+int afr_filtered_gelu_nhwc_bwd(const void *x, const void *residual, const float *scale_dev, const float *shift_dev,
+                               const void *dy, void *dz, int B, int C, int H, int W, const float *taps_up, int N_up,
+                               const float *taps_down, int N_down, int dtype, void *stream)
+{
+    return fused_nhwc(x, residual, scale_dev, shift_dev, dy, dz, B, C, H, W, taps_up, N_up, taps_down, N_down, dtype,
+                      stream, true);
+}
+
+int afr_affine_apply_nhwc(const void *x, const float *scale_dev, const float *shift_dev, void *y, int B, int C, int H, int W,
+                          int dtype, void *stream)
+{
+    if (B < 0 || C < 1 || H < 1 || W < 1) return fail(AFR_ERR_BAD_SHAPE, "bad shape");
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if (B == 0) return AFR_OK;
+    if (!x || !y || !scale_dev || !shift_dev) return fail(AFR_ERR_NULL_POINTER, "NULL pointer");
+    if (C % 4 != 0 || (reinterpret_cast<uintptr_t>(x) % (4 * esz(dtype))) != 0 || (reinterpret_cast<uintptr_t>(y) % (4 * esz(dtype))) != 0 ||
+        (reinterpret_cast<uintptr_t>(scale_dev) % 16) != 0 || (reinterpret_cast<uintptr_t>(shift_dev) % 16) != 0)
+        return fail(AFR_ERR_UNSUPPORTED, "C must be a multiple of 4 and the buffers aligned to 4 elements");
+    begin_call();
+    g_last_kernel = "affine_apply_nhwc_kernel";
+    return cuda_status(affine_apply_nhwc(x, scale_dev, shift_dev, y, B, C, (long)H * W, dtype, (cudaStream_t)stream),
+                       "affine_apply_nhwc_kernel");
+}
+
 int afr_groupnorm1_stats(const void *x, const float *gamma_dev, const float *beta_dev, float eps, const float *add_dev,
                          float *scale_dev, float *shift_dev, float *mean_dev, float *rstd_dev, int B, int C, int H, int W,
                          int dtype, void *stream)

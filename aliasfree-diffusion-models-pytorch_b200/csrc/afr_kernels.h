@@ -58,6 +58,12 @@ bool n3_fgelu_tma_supported(long planes, int H, int W, const void *const *ptrs, 
 cudaError_t n3_fgelu(const void *x, const void *res, const void *dy, const float *scale, const float *shift,
                      void *out, long planes, int H, int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB,
                      bool bwd, int dtype, bool use_tma, bool allow_sym, cudaStream_t s, const char **kernel_name);
+// channels-last ([B,H,W,C] memory, C % 32 == 0) fused forward / adjoint, symmetric taps only: cudaErrorNotSupported
+// tells the caller to use the NCHW kernels (general taps)
+bool nhwc_fgelu_supported(int C, int H, int W, const void *const *ptrs, int nptrs);
+cudaError_t nhwc_fgelu(const void *x, const void *res, const void *dy, const float *scale, const float *shift, void *out,
+                       long B, int C, int H, int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd, int dtype,
+                       cudaStream_t s);
 // up-like with N==3: in [planes,H,W] -> out [planes,2H,2W]
 bool n3_up_supported(int H, int W, const void *in, const void *out, int in_dtype, int out_dtype);
 // (C > 0: the OUTPUT is a channel slice with batch stride out_bstride elements; C == 0: dense)
@@ -106,6 +112,8 @@ cudaError_t groupnorm1_affine(const void *x, const float *gamma, const float *be
                               float *mean_out = nullptr, float *rstd_out = nullptr);
 cudaError_t affine_apply(const void *x, const float *scale, const float *shift, void *y, long planes, long hw, int dtype,
                          cudaStream_t s);
+cudaError_t affine_apply_nhwc(const void *x, const float *scale, const float *shift, void *y, long B, int C, long hw, int dtype,
+                              cudaStream_t s);
 cudaError_t ddpm_update(float *x, const float *eps, const float *noise, long n, float ca,
                         float cb, float cc, const float *table_dev, const int *step_dev, cudaStream_t s);
 

@@ -241,12 +241,31 @@ struct StepK {             // general-tap kernels
     Taps3 kU, kG, kB;
 };
 
-template <bool kBwd, class SX, class SD, typename TO>
-__device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__restrict__ out_row, int i,
+// Where a step's four outputs go: a pointer (NCHW: four adjacent columns, one 128-bit store) or an NHWC
+// position (the four columns are `cs` channels apart: four scalar stores, each coalesced across the warp's
+// 32 channels).
+template <typename T> struct NhwcOut {
+    T *p;
+    int cs;
+    __device__ __forceinline__ NhwcOut operator+(long d) const { return NhwcOut{p + d, cs}; }
+};
+template <class OUT> struct OutElem;
+template <typename T> struct OutElem<T *> { typedef T type; };
+template <typename T> struct OutElem<NhwcOut<T>> { typedef T type; };
+template <typename T> __device__ __forceinline__ void store4(T *p, float4 v) { st4(p, v); }
+__device__ __forceinline__ void st1cs(float *p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st1cs(bf16 *p, float v) { st1(p, v); }
+template <typename T> __device__ __forceinline__ void store4(const NhwcOut<T> &o, float4 v)
+{
+    st1cs(o.p, v.x); st1cs(o.p + o.cs, v.y); st1cs(o.p + 2 * o.cs, v.z); st1cs(o.p + 3 * o.cs, v.w);
+}
+
+template <bool kBwd, class SX, class SD, class OUT>
+__device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, OUT out_row, int i,
                                            bool store, bool first_col, bool any0, bool own0, const StepK &K,
                                            const RowSet &A, RowSet &B)
 {
-    constexpr bool kLow = LowMath<TO, kBwd>::value;
+    constexpr bool kLow = LowMath<typename OutElem<OUT>::type, kBwd>::value;
     const Taps3 &kU = K.kU, &kG = K.kG, &kB = K.kB;
     const float (&xa)[6] = A.x, (&da)[6] = A.d, (&mp)[9] = A.m;
     float (&xb)[6] = B.x, (&db)[6] = B.d, (&mo)[9] = B.m;
@@ -296,7 +315,7 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
         acc = fmaf(kB.k[2][2], mo[2 * q + 2], acc);
         o[q] = acc;
     }
-    if (store) st4(out_row, make_float4(o[0], o[1], o[2], o[3]));
+    if (store) store4(out_row, make_float4(o[0], o[1], o[2], o[3]));
 }
 
 // The same step for D4-symmetric taps [[a,b,a],[b',c,b'],[a,b,a]] (every filter circularLowpassKernel
@@ -364,12 +383,12 @@ __device__ __forceinline__ void sym_sums(const float (&xa)[6], const float (&ha)
     }
 }
 
-template <bool kBwd, class SX, class SD, typename TO>
-__device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__restrict__ out_row, int i,
+template <bool kBwd, class SX, class SD, class OUT>
+__device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, OUT out_row, int i,
                                            bool store, bool first_col, bool any0, bool own0, const SymK &K,
                                            const RowSet &A, RowSet &B)
 {
-    constexpr bool kLow = LowMath<TO, kBwd>::value;
+    constexpr bool kLow = LowMath<typename OutElem<OUT>::type, kBwd>::value;
     sx.load(i + 1, B.x);
     if (kBwd) sd.load(i + 1, B.d);
 #pragma unroll
@@ -428,7 +447,7 @@ __device__ __forceinline__ void strip_step(const SX &sx, const SD &sd, TO *__res
         acc = fmaf(K.dn[PH_EE], me[2 * q + 1], acc);
         o[q] = acc + ro;
     }
-    if (store) st4(out_row, make_float4(o[0], o[1], o[2], o[3]));
+    if (store) store4(out_row, make_float4(o[0], o[1], o[2], o[3]));
 }
 
 template <class KT> struct IsSym { static constexpr bool value = false; };
@@ -853,6 +872,161 @@ fgelu3_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------
+// NHWC (channels-last) flavour of the row-streaming kernel
+// ---------------------------------------------------------------------------------
+// Same strip core, different geometry.  In a channels-last tensor [B, H, W, C] the contiguous axis is C, so a
+// warp's 32 lanes are 32 CHANNELS of one 4-column strip (every load / store of the warp is one 128-byte line) and
+// the strips of a tile are the CTA's warps.  The TMA box is [32 channels, 4*strips + 2 columns, R + 1 rows,
+// P images] of the rank-4 map {C, W, H, B}; out-of-bounds columns / rows are zero-filled exactly as in the NCHW
+// kernel.  The left neighbour strip now lives in another warp, so every strip computes column 0 of its mid rows
+// itself (18 GELUs per 4 outputs instead of 16, ~11 % more instructions) -- the price of not transposing the tensor,
+// which is what PyTorch / cuDNN otherwise do around every channels-last convolution.  Symmetric taps only (every
+// filter the reference designs); other filters take the NCHW kernels through a contiguous copy.
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+struct NhwcCfg {
+    int strips, P, R;          // strips (warps) per column tile, images per CTA (strips * P == 4), rows per chunk
+    int tiles_x, cgroups;      // column tiles per image row, 32-channel groups
+    int nsegs, Hs;             // row segments (blockIdx.y) and their height
+    int tile_bytes;            // bytes of one staged box, rounded up to 128
+};
+
+template <typename T, bool kRes>
+struct NhwcRows {
+    const T *x, *r;            // staged tile at (tile row 0, halo column of this strip, this lane's channel)
+    int pitch, row0, H;        // elements per staged row; global row of tile row 0; plane height
+    float a, bl, bc, br;       // x * a + b folded into the load (b only for samples inside the plane)
+    bool aff;
+    __device__ __forceinline__ void load(int row, float (&v)[6]) const
+    {
+        const int off = (row - row0) * pitch;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = lds1(x + off + 32 * k);
+        if (aff) {
+            const bool in = (unsigned)row < (unsigned)H;       // staged zeros (OOB fill) times a stay zero
+            v[0] = fmaf(v[0], a, in ? bl : 0.f);
+#pragma unroll
+            for (int k = 1; k < 5; ++k) v[k] = fmaf(v[k], a, in ? bc : 0.f);
+            v[5] = fmaf(v[5], a, in ? br : 0.f);
+        }
+        if (kRes) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v[k] += lds1(r + off + 32 * k);
+        }
+    }
+};
+
+template <typename T, bool kBwd, bool kRes>
+__global__ void __launch_bounds__(128)
+fgelu3_nhwc_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mres,
+                   const __grid_constant__ CUtensorMap mdy, const float *__restrict__ scale,
+                   const float *__restrict__ shift, T *__restrict__ out, int B, int C, int H, int W,
+                   const __grid_constant__ NhwcCfg cfg, const __grid_constant__ SymK K)
+{
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ __align__(8) uint64_t full[2];
+    constexpr int NIN = 1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0);
+
+    const int cg = (int)(blockIdx.x % cfg.cgroups);
+    const int rest = (int)(blockIdx.x / cfg.cgroups);
+    const int tx = rest % cfg.tiles_x;
+    const int b0 = (rest / cfg.tiles_x) * cfg.P;
+    const int Tw = 4 * cfg.strips, j0 = tx * Tw, cols = Tw + 2, rows = cfg.R + 1;
+    const int pitch = cols * 32, img_elems = rows * pitch;
+    const int stage_bytes = NIN * cfg.tile_bytes;
+    const uint32_t box_bytes = (uint32_t)(img_elems * cfg.P * sizeof(T));
+
+    const int seg_lo = (int)blockIdx.y * cfg.Hs;
+    const int seg_hi = min(H, seg_lo + cfg.Hs);
+    const int istart = seg_lo > 0 ? seg_lo - 1 : 0;
+    const int nchunks = (seg_hi - istart + cfg.R - 1) / cfg.R;
+
+    auto issue = [&](int k) {
+        unsigned char *base = tile_smem + (k & 1) * stage_bytes;
+        uint64_t *bar = &full[k & 1];
+        const int row = istart + k * cfg.R;
+        mbar_expect_tx(bar, box_bytes * NIN);
+        tma_load_4d(base, &mx, bar, cg * 32, j0 - 1, row, b0);
+        if (kRes) tma_load_4d(base + cfg.tile_bytes, &mres, bar, cg * 32, j0 - 1, row, b0);
+        if (kBwd) tma_load_4d(base + (kRes ? 2 : 1) * cfg.tile_bytes, &mdy, bar, cg * 32, j0 - 1, row, b0);
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        issue(0);
+        if (nchunks > 1) issue(1);
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = warp % cfg.strips, pl = warp / cfg.strips;
+    const int j = j0 + 4 * s, c = cg * 32 + lane;
+    const bool valid = (b0 + pl < B) && (j < W);
+    const int b = (b0 + pl < B) ? b0 + pl : b0;               // idle warps shadow image b0, stores off
+    const int spl = (b0 + pl < B) ? pl : 0;
+    const bool first_col = (j == 0);
+    const bool own0 = (j > 0);                                  // no left neighbour in this warp: always recompute
+    const int toff = spl * img_elems + (4 * s) * 32 + lane;     // box column 0 is global column j0 - 1
+    const long rowstride = (long)W * C;
+    const NhwcOut<T> dst{out + ((long)b * H * W + (valid ? j : 0)) * C + c, C};
+    float a = 1.f, bsh = 0.f;
+    const bool aff = scale != nullptr;
+    if (aff) { a = __ldg(scale + (long)b * C + c); bsh = __ldg(shift + (long)b * C + c); }
+    const float bl = (j > 0 && j <= W) ? bsh : 0.f, bc = (j < W) ? bsh : 0.f, br = (j + 4 < W) ? bsh : 0.f;
+
+    RowSet S0, S1;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { S0.d[q] = 0.f; S1.d[q] = 0.f; }
+    clear_carry(S0);
+
+    for (int k = 0; k < nchunks; ++k) {
+        const unsigned char *base = tile_smem + (k & 1) * stage_bytes;
+        const T *xs = reinterpret_cast<const T *>(base);
+        const T *rs = reinterpret_cast<const T *>(base + (kRes ? cfg.tile_bytes : 0));
+        const T *ds = reinterpret_cast<const T *>(base + (kRes ? 2 : 1) * cfg.tile_bytes);
+        const int r0 = istart + k * cfg.R;
+        mbar_wait(&full[k & 1], (k >> 1) & 1);
+        if (k == 0) {
+            NhwcRows<T, kRes> sx{xs + toff, rs + toff, pitch, r0, H, a, bl, bc, br, aff};
+            NhwcRows<T, false> sd{ds + toff, nullptr, pitch, r0, H, 1.f, 0.f, 0.f, 0.f, false};
+            strip_begin<kBwd, SymK>(sx, sd, r0, S0);
+        }
+        const int rend = min(r0 + cfg.R, seg_hi + ((seg_hi - r0) & 1));
+        const T *xr = xs + toff + pitch, *rr = rs + toff + pitch, *dr = ds + toff + pitch;
+        NhwcOut<T> orow = dst + (long)r0 * rowstride;
+        for (int i = r0; i < rend; i += 2) {
+            {
+                NhwcRows<T, kRes> sx{xr, rr, pitch, i + 1, H, a, bl, bc, br, aff};
+                NhwcRows<T, false> sd{dr, nullptr, pitch, i + 1, H, 1.f, 0.f, 0.f, 0.f, false};
+                strip_step<kBwd>(sx, sd, orow, i, valid && i >= seg_lo && i < seg_hi, first_col, true, own0, K, S0, S1);
+            }
+            {
+                NhwcRows<T, kRes> sx{xr + pitch, rr + pitch, pitch, i + 2, H, a, bl, bc, br, aff};
+                NhwcRows<T, false> sd{dr + pitch, nullptr, pitch, i + 2, H, 1.f, 0.f, 0.f, 0.f, false};
+                strip_step<kBwd>(sx, sd, orow + rowstride, i + 1, valid && i + 1 >= seg_lo && i + 1 < seg_hi, first_col,
+                                 true, own0, K, S1, S0);
+            }
+            xr += 2 * pitch; rr += 2 * pitch; dr += 2 * pitch;
+            orow = orow + 2 * rowstride;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && k + 2 < nchunks) issue(k + 2);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // standalone N == 3 resamplers (HBM-bound)
 // ---------------------------------------------------------------------------------
 // up-like: thread = 4 input columns -> 8 output columns, two output rows per input row
@@ -1156,12 +1330,13 @@ static EncodeTiledFn encode_tiled_fn()
 // state -- SURVEY.md section 8b).  AFR_NO_DESC_CACHE=1 disables it (A/B timing).
 struct MapKey {
     const void *base;
-    long planes;
+    long planes;               // planes (rank-3 NCHW map) or images (rank-4 NHWC map)
     int H, W, dtype, bw, bh, bp;
+    int C;                     // 0: rank-3 map over [planes, H, W]; > 0: rank-4 map over [B, H, W, C]
     bool operator==(const MapKey &o) const
     {
         return base == o.base && planes == o.planes && H == o.H && W == o.W && dtype == o.dtype && bw == o.bw &&
-               bh == o.bh && bp == o.bp;
+               bh == o.bh && bp == o.bp && C == o.C;
     }
 };
 struct MapSlot {
@@ -1204,22 +1379,54 @@ static bool encode_plane_map(CUtensorMap *m, const void *base, long planes, int 
     return r == CUDA_SUCCESS;
 }
 
-static bool make_plane_map(CUtensorMap *m, const void *base, long planes, int H, int W, int dtype,
-                           int box_w, int box_h, int box_p)
+// rank-4 map over a channels-last tensor: dims {C, W, H, B}, box {32 channels, box_w columns, box_h rows, box_p images}
+static bool encode_nhwc_map(CUtensorMap *m, const void *base, long B, int C, int H, int W, int dtype, int box_w, int box_h,
+                            int box_p)
 {
-    if (desc_cache_disabled()) return encode_plane_map(m, base, planes, H, W, dtype, box_w, box_h, box_p);
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { set_detail("cuTensorMapEncodeTiled entry point not found"); return false; }
+    const size_t es = esize(dtype);
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+    cuuint32_t box[4] = {32u, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_p};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = CUDA_SUCCESS;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        r = enc(m, dtype == AFR_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+        cudaFree(0);                               // bind the primary context on a fresh thread (see encode_plane_map)
+    }
+    if (r != CUDA_SUCCESS)
+        set_detail("cuTensorMapEncodeTiled (NHWC) failed (CUresult %d) base=%p dims=[%d,%d,%d,%ld] box=[32,%d,%d,%d]", (int)r,
+                   base, C, W, H, B, box_w, box_h, box_p);
+    return r == CUDA_SUCCESS;
+}
+
+static bool make_plane_map(CUtensorMap *m, const void *base, long planes, int H, int W, int dtype,
+                           int box_w, int box_h, int box_p, int C = 0)
+{
+    if (desc_cache_disabled())
+        return C > 0 ? encode_nhwc_map(m, base, planes, C, H, W, dtype, box_w, box_h, box_p)
+                     : encode_plane_map(m, base, planes, H, W, dtype, box_w, box_h, box_p);
     // allocated on a thread's first TMA launch, freed with the thread (over-aligned type: aligned operator new)
     static thread_local std::unique_ptr<MapSlot[]> slots;
     if (!slots) slots.reset(new (std::nothrow) MapSlot[kMapSlots]());
-    if (!slots) return encode_plane_map(m, base, planes, H, W, dtype, box_w, box_h, box_p);
-    const MapKey key = {base, planes, H, W, dtype, box_w, box_h, box_p};
+    if (!slots)
+        return C > 0 ? encode_nhwc_map(m, base, planes, C, H, W, dtype, box_w, box_h, box_p)
+                     : encode_plane_map(m, base, planes, H, W, dtype, box_w, box_h, box_p);
+    const MapKey key = {base, planes, H, W, dtype, box_w, box_h, box_p, C};
     uint64_t h = (uint64_t)reinterpret_cast<uintptr_t>(base) >> 8;     // allocations are 512-byte aligned
     h ^= (uint64_t)planes * 0x9E3779B97F4A7C15ull;
-    h ^= ((uint64_t)H << 40) ^ ((uint64_t)W << 20) ^ ((uint64_t)box_h << 8) ^ (uint64_t)box_p ^ ((uint64_t)dtype << 60);
+    h ^= ((uint64_t)H << 40) ^ ((uint64_t)W << 20) ^ ((uint64_t)box_h << 8) ^ (uint64_t)box_p ^ ((uint64_t)dtype << 60) ^
+         ((uint64_t)C << 30);
     h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
     MapSlot &sl = slots[h % kMapSlots];
     if (sl.valid && sl.key == key) { *m = sl.map; return true; }
-    if (!encode_plane_map(m, base, planes, H, W, dtype, box_w, box_h, box_p)) return false;
+    if (!(C > 0 ? encode_nhwc_map(m, base, planes, C, H, W, dtype, box_w, box_h, box_p)
+                : encode_plane_map(m, base, planes, H, W, dtype, box_w, box_h, box_p)))
+        return false;
     sl.key = key; sl.map = *m; sl.valid = true;
     return true;
 }
@@ -1501,6 +1708,86 @@ cudaError_t n3_down_like(const void *in, void *out, long planes, int H, int W, c
         down3_kernel<bf16, 4><<<(unsigned)grid, 256, 0, s>>>((const bf16 *)in, (bf16 *)out, planes, H,
                                                              W, Ho, Wo, strips, nseg, R, C, in_bstride, k);
     return cudaGetLastError();
+}
+
+// ---- NHWC host side ------------------------------------------------------------------------------------
+bool nhwc_fgelu_supported(int C, int H, int W, const void *const *ptrs, int nptrs)
+{
+    if (C < 32 || (C % 32) != 0 || H < 2 || W < 4 || (W % 4) != 0) return false;
+    for (int i = 0; i < nptrs; ++i)
+        if (ptrs[i] && !aligned_to(ptrs[i], 16)) return false;
+    return true;
+}
+
+static bool pick_nhwc(long B, int C, int H, int W, int dtype, int nin, NhwcCfg *cfg)
+{
+    const size_t es = esize(dtype);
+    NhwcCfg c;
+    c.strips = W >= 12 ? 4 : (W >= 8 ? 2 : 1);
+    c.P = 4 / c.strips;
+    c.tiles_x = (W + 4 * c.strips - 1) / (4 * c.strips);
+    c.cgroups = C / 32;
+    for (c.R = 8; c.R >= 2; c.R /= 2) {
+        const size_t bytes = (size_t)32 * (4 * c.strips + 2) * (c.R + 1) * c.P * es;
+        c.tile_bytes = (int)((bytes + 127) / 128 * 128);
+        if ((size_t)c.tile_bytes * nin * 2 <= ring_budget_bytes() || c.R == 2) break;
+    }
+    if ((size_t)c.tile_bytes * nin * 2 > 96 * 1024) return false;
+    const long ctas = (B + c.P - 1) / c.P * c.tiles_x * c.cgroups;
+    long resident = (long)(220 * 1024) / ((long)c.tile_bytes * nin * 2);
+    resident = resident < 1 ? 1 : (resident > 5 ? 5 : resident);
+    c.nsegs = 1;
+    while (2 * ctas * c.nsegs < 5 * 148 * resident && H / (c.nsegs * 2) >= 2 * c.R && c.nsegs < 16) c.nsegs *= 2;
+    c.Hs = ((H + c.nsegs - 1) / c.nsegs + c.R - 1) / c.R * c.R;
+    c.nsegs = (H + c.Hs - 1) / c.Hs;
+    *cfg = c;
+    return true;
+}
+
+template <typename T, bool kBwd, bool kRes>
+static cudaError_t launch_nhwc(const void *x, const void *res, const void *dy, const float *scale, const float *shift,
+                               void *out, long B, int C, int H, int W, int dtype, const SymK &K, cudaStream_t s)
+{
+    const int nin = 1 + (kRes ? 1 : 0) + (kBwd ? 1 : 0);
+    NhwcCfg cfg;
+    if (!pick_nhwc(B, C, H, W, dtype, nin, &cfg)) { set_detail("no NHWC tile configuration"); return cudaErrorInvalidConfiguration; }
+    CUtensorMap mx, mres, mdy;
+    const int bw = 4 * cfg.strips + 2, bh = cfg.R + 1;
+    if (!make_plane_map(&mx, x, B, H, W, dtype, bw, bh, cfg.P, C)) return cudaErrorInvalidValue;
+    mres = mx; mdy = mx;
+    if (kRes && !make_plane_map(&mres, res, B, H, W, dtype, bw, bh, cfg.P, C)) return cudaErrorInvalidValue;
+    if (kBwd && !make_plane_map(&mdy, dy, B, H, W, dtype, bw, bh, cfg.P, C)) return cudaErrorInvalidValue;
+    const long grid = (B + cfg.P - 1) / cfg.P * cfg.tiles_x * cfg.cgroups;
+    if (grid > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+    const size_t smem = (size_t)cfg.tile_bytes * nin * 2;
+    auto kern = fgelu3_nhwc_kernel<T, kBwd, kRes>;
+    static std::atomic<unsigned long long> attr_done{0};
+    if (cudaError_t ae = ensure_dyn_smem(kern, attr_done, 100 * 1024)) { set_detail("cudaFuncSetAttribute(max dynamic smem) failed"); return ae; }
+    kern<<<dim3((unsigned)grid, (unsigned)cfg.nsegs), 128, smem, s>>>(mx, mres, mdy, scale, shift, (T *)out, (int)B, C, H, W, cfg, K);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) set_detail("NHWC launch grid=%ld smem=%zu strips=%d R=%d P=%d", grid, smem, cfg.strips, cfg.R, cfg.P);
+    return e;
+}
+
+// channels-last fused forward / adjoint.  Returns cudaErrorNotSupported when the taps are not D4-symmetric (or, in
+// the forward, the up filter has a negative tap): the caller then takes the NCHW kernels.
+cudaError_t nhwc_fgelu(const void *x, const void *res, const void *dy, const float *scale, const float *shift, void *out,
+                       long B, int C, int H, int W, const Taps3 &kU, const Taps3 &kG, const Taps3 &kB, bool bwd, int dtype,
+                       cudaStream_t s)
+{
+    SymK KS;
+    if (!make_sym(kU, kG, kB, bwd, dtype == AFR_BF16 && AFR_BF16_LOW_FWD, &KS)) return cudaErrorNotSupported;
+    if (B > 0x7fffffffL) return cudaErrorInvalidConfiguration;
+#define AFR_NH(T)                                                                                                   \
+    do {                                                                                                            \
+        if (bwd) return res ? launch_nhwc<T, true, true>(x, res, dy, scale, shift, out, B, C, H, W, dtype, KS, s)     \
+                            : launch_nhwc<T, true, false>(x, res, dy, scale, shift, out, B, C, H, W, dtype, KS, s);   \
+        return res ? launch_nhwc<T, false, true>(x, res, dy, scale, shift, out, B, C, H, W, dtype, KS, s)            \
+                   : launch_nhwc<T, false, false>(x, res, dy, scale, shift, out, B, C, H, W, dtype, KS, s);          \
+    } while (0)
+    if (dtype == AFR_F32) AFR_NH(float);
+    AFR_NH(bf16);
+#undef AFR_NH
 }
 
 }  // namespace afr

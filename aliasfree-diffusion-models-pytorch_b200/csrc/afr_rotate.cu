@@ -182,6 +182,38 @@ affine_apply_kernel(const T *__restrict__ x, const float *__restrict__ scale, co
     }
 }
 
+// channels-last flavour: element i of sample b belongs to channel i % C; four consecutive elements are four channels
+template <typename T>
+__global__ void __launch_bounds__(256)
+affine_apply_nhwc_kernel(const T *__restrict__ x, const float *__restrict__ scale, const float *__restrict__ shift,
+                         T *__restrict__ y, long total4, int C4, long sample4)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += stride) {
+        const long b = i / sample4;
+        const int c4 = (int)((i - b * sample4) % C4);
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(scale) + b * C4 + c4);
+        const float4 s = __ldg(reinterpret_cast<const float4 *>(shift) + b * C4 + c4);
+        float4 v = ldv4<T>(x + 4 * i);
+        v.x = fmaf(v.x, a.x, s.x); v.y = fmaf(v.y, a.y, s.y); v.z = fmaf(v.z, a.z, s.z); v.w = fmaf(v.w, a.w, s.w);
+        st4(y + 4 * i, v);
+    }
+}
+
+cudaError_t affine_apply_nhwc(const void *x, const float *scale, const float *shift, void *y, long B, int C, long hw, int dtype,
+                              cudaStream_t s)
+{
+    const long sample4 = hw * C / 4, total4 = B * sample4;
+    long grid = (total4 + 255) / 256;
+    if (grid < 1) grid = 1;
+    if (grid > 148 * 32) grid = 148 * 32;
+    if (dtype == AFR_F32)
+        affine_apply_nhwc_kernel<float><<<(unsigned)grid, 256, 0, s>>>((const float *)x, scale, shift, (float *)y, total4, C / 4, sample4);
+    else
+        affine_apply_nhwc_kernel<bf16><<<(unsigned)grid, 256, 0, s>>>((const bf16 *)x, scale, shift, (bf16 *)y, total4, C / 4, sample4);
+    return cudaGetLastError();
+}
+
 cudaError_t affine_apply(const void *x, const float *scale, const float *shift, void *y, long planes, long hw, int dtype,
                          cudaStream_t s)
 {

@@ -53,7 +53,18 @@ class _on_device:
         return False
 
 
-def _require(x, name="x"):
+def _is_cl(x):
+    """Dense channels-last memory ([B, H, W, C]) that is not also dense NCHW (C == 1 or H == W == 1 are both)."""
+    return x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+
+
+def _nhwc_eligible(x, ku, kd):
+    """Shapes the channels-last fused kernel takes (csrc/afr_n3.cu: fgelu3_nhwc_kernel)."""
+    return (_is_cl(x) and ku.n == 3 and kd.n == 3 and x.shape[1] % 32 == 0 and x.shape[3] % 4 == 0 and x.shape[2] >= 2
+            and x.dtype in _DT)
+
+
+def _require(x, name="x", keep_cl=False):
     if not isinstance(x, torch.Tensor):
         raise TypeError("afr: %s must be a torch.Tensor" % name)
     if not x.is_cuda:
@@ -62,6 +73,8 @@ def _require(x, name="x"):
         raise ValueError("afr: %s must be [B, C, H, W], got %s" % (name, tuple(x.shape)))
     if x.dtype not in _DT:
         raise TypeError("afr: %s dtype %s unsupported (float32 / bfloat16)" % (name, x.dtype))
+    if keep_cl and _is_cl(x):
+        return x                      # channels-last stays channels-last where a kernel can take it as it is
     return x.contiguous()
 
 
@@ -126,7 +139,41 @@ def _down_bwd(dy, k, H, W):
     return dv
 
 
+def _fgelu_nhwc(x, res, scale, shift, dy, ku, kd):
+    """Channels-last launch (forward, or adjoint when `dy` is given; optional GroupNorm affine).  Returns the
+    channels-last result, or None when the library declines (filters that are not D4-symmetric): the caller then
+    goes through NCHW-contiguous copies."""
+    B, C, H, W = x.shape
+    cl = torch.channels_last
+    if res is not None:
+        res = res.contiguous(memory_format=cl)
+    out = torch.empty_like(x, memory_format=cl)
+    L = _native.lib()
+    with _on_device(x.device):
+        if dy is None:
+            rc = L.afr_filtered_gelu_nhwc_fwd(x.data_ptr(), None if res is None else res.data_ptr(),
+                                              None if scale is None else scale.data_ptr(),
+                                              None if shift is None else shift.data_ptr(), out.data_ptr(), B, C, H, W,
+                                              ku.ptr, ku.n, kd.ptr, kd.n, _DT[x.dtype], _stream(x))
+        else:
+            dy = dy.contiguous(memory_format=cl).to(x.dtype)
+            rc = L.afr_filtered_gelu_nhwc_bwd(x.data_ptr(), None if res is None else res.data_ptr(),
+                                              None if scale is None else scale.data_ptr(),
+                                              None if shift is None else shift.data_ptr(), dy.data_ptr(), out.data_ptr(),
+                                              B, C, H, W, ku.ptr, ku.n, kd.ptr, kd.n, _DT[x.dtype], _stream(x))
+    if rc == 7:                                   # AFR_ERR_UNSUPPORTED
+        return None
+    _check(rc)
+    return out
+
+
 def _fgelu_fwd(x, res, ku, kd, out=None):
+    if out is None and _nhwc_eligible(x, ku, kd) and (res is None or res.dtype == x.dtype):
+        y = _fgelu_nhwc(x, res, None, None, None, ku, kd)
+        if y is not None:
+            return y
+    x = x.contiguous()
+    res = None if res is None else res.contiguous()
     B, C, H, W = x.shape
     y = torch.empty_like(x) if out is None else out
     with _on_device(x.device):
@@ -137,6 +184,12 @@ def _fgelu_fwd(x, res, ku, kd, out=None):
 
 
 def _fgelu_bwd(x, res, dy, ku, kd):
+    if _nhwc_eligible(x, ku, kd) and (res is None or res.dtype == x.dtype):
+        dx = _fgelu_nhwc(x, res, None, None, dy, ku, kd)
+        if dx is not None:
+            return dx
+    x, dy = x.contiguous(), dy.contiguous()
+    res = None if res is None else res.contiguous()
     B, C, H, W = x.shape
     dx = torch.empty_like(x)
     with _on_device(x.device):
@@ -197,7 +250,7 @@ class _FilteredGelu(torch.autograd.Function):
     def backward(ctx, dy):
         saved = ctx.saved_tensors
         x, res = saved[0], (saved[1] if ctx.has_res else None)
-        dx = _fgelu_bwd(x, res, dy.contiguous().to(x.dtype), ctx.ku, ctx.kd)
+        dx = _fgelu_bwd(x, res, dy.to(x.dtype), ctx.ku, ctx.kd)
         return dx, (dx if ctx.has_res else None), None, None
 
 
@@ -249,7 +302,7 @@ def up2x_cat(skip, x, filt):
 def _match_residual(x, residual):
     """``x + residual`` follows PyTorch type promotion (e.g. bf16 conv output + fp32 skip under
     autocast -> fp32), like the reference's ``x = x + residual`` (modules/ddpm_utils.py:128)."""
-    residual = _require(residual, "residual")
+    residual = _require(residual, "residual", keep_cl=True)
     if residual.shape != x.shape:
         raise ValueError("afr: residual must match x in shape")
     if residual.dtype != x.dtype:
@@ -276,7 +329,7 @@ def down2x(x, filt):
 def filtered_gelu(x, filt_up, filt_down, residual=None):
     """down2x(gelu(up2x(x + residual, filt_up)), filt_down) in ONE kernel (exact erf GELU).
     Replaces modules/ddpm_utils.py:123-125 / 128-131 / 137-139."""
-    x = _require(x)
+    x = _require(x, keep_cl=True)
     if residual is not None:
         x, residual = _match_residual(x, residual)
     if not _needs_grad(x, residual):
@@ -413,9 +466,12 @@ def _gn_stats(h, weight, bias, eps, add=None):
 
 
 def _gn_backward(dz, h, mean, rstd, weight):
-    """GroupNorm(1, C) backward (dz = gradient of the normalised + affine output): ATen's own kernels."""
+    """GroupNorm(1, C) backward (dz = gradient of the normalised + affine output): ATen's own kernels.  Called
+    directly, the ATen op reads its tensors as dense NCHW whatever their strides (measured: channels-last inputs give
+    dgamma / dbeta that are off by O(1)), so channels-last tensors are made NCHW-contiguous first."""
     B, C, H, W = h.shape
-    return torch.ops.aten.native_group_norm_backward(dz, h, mean, rstd, weight, B, C, H * W, 1, [True, True, True])
+    return torch.ops.aten.native_group_norm_backward(dz.contiguous(), h.contiguous(), mean, rstd, weight, B, C, H * W, 1,
+                                                     [True, True, True])
 
 
 class _NormFilteredGelu(torch.autograd.Function):
@@ -426,7 +482,16 @@ class _NormFilteredGelu(torch.autograd.Function):
     @staticmethod
     def run(h, weight, bias, eps, res, ku, kd):
         B, C, H, W = h.shape
-        scale, shift, mean, rstd = _gn_stats(h, weight, bias, eps)
+        if _is_cl(h) and not _nhwc_eligible(h, ku, kd):
+            h = h.contiguous()
+        scale, shift, mean, rstd = _gn_stats(h, weight, bias, eps)        # layout-agnostic: a sample is one dense block
+        if _nhwc_eligible(h, ku, kd):
+            y = _fgelu_nhwc(h, res, scale, shift, None, ku, kd)
+            if y is not None:
+                return y, scale, shift, mean, rstd
+            h = h.contiguous()
+            scale, shift, mean, rstd = _gn_stats(h, weight, bias, eps)
+        res = None if res is None else res.contiguous()
         y = torch.empty_like(h)
         with _on_device(h.device):
             _check(_native.lib().afr_filtered_gelu_affine_fwd(
@@ -447,6 +512,14 @@ class _NormFilteredGelu(torch.autograd.Function):
         h, weight, scale, shift, mean, rstd = ctx.saved_tensors[:6]
         res = ctx.saved_tensors[6] if ctx.has_res else None
         B, C, H, W = h.shape
+        dz = None
+        if _nhwc_eligible(h, ctx.ku, ctx.kd):
+            dz = _fgelu_nhwc(h, res, scale, shift, dy, ctx.ku, ctx.kd)
+        if dz is not None:
+            dh, dw, db = _gn_backward(dz, h, mean, rstd, weight)
+            return dh, dw, db, None, (dz if ctx.has_res else None), None, None
+        h = h.contiguous()
+        res = None if res is None else res.contiguous()
         dz = torch.empty_like(h)
         dy = dy.contiguous().to(h.dtype)
         with _on_device(h.device):
@@ -464,10 +537,13 @@ class _NormAddEmb(torch.autograd.Function):
     def run(h, weight, bias, eps, emb):
         B, C, H, W = h.shape
         scale, shift, mean, rstd = _gn_stats(h, weight, bias, eps, add=emb)
-        y = torch.empty_like(h)
+        y = torch.empty_like(h)                                        # keeps h's memory format
+        apply = _native.lib().afr_affine_apply_nhwc if (_is_cl(h) and C % 4 == 0) else _native.lib().afr_affine_apply
+        if _is_cl(h) and C % 4 != 0:
+            h = h.contiguous()
+            y = torch.empty_like(h)
         with _on_device(h.device):
-            _check(_native.lib().afr_affine_apply(h.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B, C, H, W,
-                                                  _DT[h.dtype], _stream(h)))
+            _check(apply(h.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), B, C, H, W, _DT[h.dtype], _stream(h)))
         return y, mean, rstd
 
     @staticmethod
@@ -502,9 +578,9 @@ def norm_fusable(h, norm, n_up=3, n_down=3):
 def norm_filtered_gelu(h, norm, filt_up, filt_down, residual=None):
     """``filtered_gelu(norm(h) + residual)`` for a ``GroupNorm(1, C)`` module `norm` (modules/ddpm_utils.py:122-125,
     127-131) without writing the normalised tensor; differentiable.  Check ``norm_fusable`` first."""
-    h = _require(h, "h")
+    h = _require(h, "h", keep_cl=True)
     if residual is not None:
-        residual = _require(residual, "residual")
+        residual = _require(residual, "residual", keep_cl=True)
         if residual.dtype != h.dtype or residual.shape != h.shape:
             raise ValueError("afr: residual must match h in shape and dtype")
     if not _needs_grad(h, residual, norm.weight, norm.bias):
@@ -515,7 +591,7 @@ def norm_filtered_gelu(h, norm, filt_up, filt_down, residual=None):
 def norm_add_emb(h, norm, emb):
     """``norm(h) + emb[:, :, None, None]`` (the tail of every Down / Up stage, modules/ddpm_utils.py:385-387,
     415-417: GroupNorm, ``.repeat`` of the time embedding, add) in one statistics kernel + one apply pass."""
-    h = _require(h, "h")
+    h = _require(h, "h", keep_cl=True)
     if emb.dim() != 2 or tuple(emb.shape) != tuple(h.shape[:2]):
         raise ValueError("afr: emb must be [B, C]")
     if not _needs_grad(h, emb, norm.weight, norm.bias):

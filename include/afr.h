@@ -153,6 +153,25 @@ int afr_filtered_gelu_affine_bwd(const void *x, const void *residual, const floa
                                  const float *taps_up, int N_up, const float *taps_down, int N_down,
                                  int dtype, void *stream);
 
+/* Channels-last (NHWC memory: x[b][h][w][c], what `tensor.contiguous(memory_format=torch.channels_last)` holds)
+ * flavours of the fused filtered nonlinearity, so that a UNet run in channels-last -- where cuDNN needs no
+ * nchw<->nhwc conversion kernels around its convolutions -- does not have to transpose for this op either.
+ * Same function as afr_filtered_gelu_fwd / _bwd with the optional GroupNorm affine of ..._affine_fwd / _bwd
+ * (scale_dev / shift_dev: DEVICE fp32 [B*C], or both NULL); B, C, H, W are the LOGICAL dims.  Requires 3x3
+ * D4-symmetric filters (every circularLowpassKernel filter), C % 32 == 0, W % 4 == 0, H >= 2 and 16-byte aligned
+ * buffers; AFR_ERR_UNSUPPORTED otherwise (callers then make the tensor NCHW-contiguous and use the entry points above). */
+int afr_filtered_gelu_nhwc_fwd(const void *x, const void *residual, const float *scale_dev,
+                               const float *shift_dev, void *y, int B, int C, int H, int W,
+                               const float *taps_up, int N_up, const float *taps_down, int N_down,
+                               int dtype, void *stream);
+int afr_filtered_gelu_nhwc_bwd(const void *x, const void *residual, const float *scale_dev,
+                               const float *shift_dev, const void *dy, void *dz, int B, int C, int H, int W,
+                               const float *taps_up, int N_up, const float *taps_down, int N_down,
+                               int dtype, void *stream);
+/* afr_affine_apply for channels-last memory (C % 4 == 0). */
+int afr_affine_apply_nhwc(const void *x, const float *scale_dev, const float *shift_dev, void *y,
+                          int B, int C, int H, int W, int dtype, void *stream);
+
 /* adjoint of the above wrt (x + residual): recomputes u from x, reads dy, writes dx
  * (d/dx and d/dresidual are the same tensor).  No saved 4x intermediates. */
 int afr_filtered_gelu_bwd(const void *x, const void *residual, const void *dy, void *dx,

@@ -517,6 +517,84 @@ def test_gelu_down2x_variant4(afr, oracle, shape, dtype):
             afr.ops.gelu_down2x_affine(vt, scale, shift, k)
 
 
+NHWC_SHAPES = [(2, 32, 16, 16), (1, 64, 64, 64), (3, 96, 5, 12), (5, 32, 4, 4), (2, 128, 8, 8), (1, 32, 2, 24), (2, 64, 33, 40),
+               (7, 32, 8, 4), (1, 32, 130, 20)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("shape", NHWC_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_channels_last_fused_kernel(afr, oracle, shape, dtype):
+    """Channels-last tensors go through fgelu3_nhwc_kernel without a layout copy: forward, adjoint, fused residual,
+    autograd, output stays channels-last; checked against the oracle (which is layout-free) and the NCHW kernels."""
+    B, C, H, W = shape
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    rng = np.random.default_rng(C + H * 7 + W)
+    k = oracle.lowpass_taps(np.pi / 2, 3, 2.0)
+    kd = oracle.lowpass_taps(0.7 * np.pi, 3, 1.0)
+    cl = torch.channels_last
+    x = dev(rng.standard_normal(shape).astype(np.float32), dtype).contiguous(memory_format=cl)
+    r = dev(rng.standard_normal(shape).astype(np.float32), dtype).contiguous(memory_format=cl)
+    dy = dev(rng.standard_normal(shape).astype(np.float32), dtype)
+    x32, r32, dy32 = host(x), host(r), host(dy)
+    xt, rt = x.clone(memory_format=cl).requires_grad_(True), r.clone(memory_format=cl).requires_grad_(True)
+    y = afr.filtered_gelu(xt, k, kd)
+    assert afr.last_kernel() == "fgelu3_nhwc_kernel<sym>"
+    assert y.is_contiguous(memory_format=cl) and tuple(y.shape) == shape
+    assert relmax(host(y), oracle.filtered_gelu(x32, k, kd)) <= tol
+    (gx,) = torch.autograd.grad(y, xt, dy)
+    assert relmax(host(gx), oracle.filtered_gelu_bwd(x32, dy32, k, kd)) <= tol
+    y2 = afr.filtered_gelu(xt, k, kd, residual=rt)
+    assert relmax(host(y2), oracle.filtered_gelu(x32 + r32, k, kd)) <= tol
+    gx2, gr2 = torch.autograd.grad(y2, (xt, rt), dy.contiguous(memory_format=cl))
+    assert relmax(host(gx2), oracle.filtered_gelu_bwd(x32 + r32, dy32, k, kd)) <= tol and torch.equal(gx2, gr2)
+    # same values as the NCHW kernels on the same data (different summation order inside a step: tiny differences)
+    yn = afr.filtered_gelu(x.contiguous(), k, kd)
+    assert afr.last_kernel() != "fgelu3_nhwc_kernel<sym>"
+    assert relmax(host(y), host(yn)) <= (2e-6 if dtype == torch.float32 else tol)
+    # filters the channels-last kernel does not take (asymmetric taps) still work, through a contiguous copy
+    ka = k.copy(); ka[0, 1] += 0.01
+    ya = afr.filtered_gelu(x, ka, kd)
+    assert relmax(host(ya), oracle.filtered_gelu(x32, ka, kd)) <= tol
+
+
+def test_channels_last_groupnorm_fold_and_embedding(afr, oracle):
+    """The GroupNorm fold and the embedding fold on channels-last tensors: same values and gradients as the NCHW path."""
+    from aliasfree_b200 import ops
+    torch.manual_seed(5)
+    cl = torch.channels_last
+    k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
+    norm = torch.nn.GroupNorm(1, 64).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.2 * torch.randn(64)); norm.bias.copy_(0.3 * torch.randn(64))
+    h = torch.randn(3, 64, 12, 16, device="cuda")
+    res = torch.randn_like(h); emb = torch.randn(3, 64, device="cuda"); dy = torch.randn_like(h)
+    outs = {}
+    for fmt in ("nchw", "nhwc"):
+        conv = (lambda t: t.contiguous(memory_format=cl)) if fmt == "nhwc" else (lambda t: t.contiguous())
+        hh, rr = conv(h).clone().requires_grad_(True), conv(res).clone().requires_grad_(True)
+        ee = emb.clone().requires_grad_(True)
+        for p_ in norm.parameters():
+            p_.grad = None
+        y = ops.norm_filtered_gelu(hh, norm, k, k, residual=rr)
+        kern = afr.last_kernel()
+        z = ops.norm_add_emb(hh, norm, ee)
+        kern_z = afr.last_kernel()
+        (y * dy).sum().backward(retain_graph=True)
+        g1 = (hh.grad.clone(), rr.grad.clone(), norm.weight.grad.clone(), norm.bias.grad.clone())
+        hh.grad = None; norm.weight.grad = None; norm.bias.grad = None
+        (z * dy).sum().backward()
+        outs[fmt] = (y.detach(), z.detach(), g1, (hh.grad.clone(), ee.grad.clone(), norm.weight.grad.clone()), kern, kern_z,
+                     y.is_contiguous(memory_format=cl) and not y.is_contiguous())
+    assert outs["nhwc"][4] == "fgelu3_nhwc_kernel<sym>" and outs["nhwc"][5] == "affine_apply_nhwc_kernel" and outs["nhwc"][6]
+    assert outs["nchw"][4] != "fgelu3_nhwc_kernel<sym>" and outs["nchw"][5] == "affine_apply_kernel" and not outs["nchw"][6]
+    want = torch.nn.functional.group_norm(h, 1, norm.weight, norm.bias, norm.eps) + res
+    assert relmax(host(outs["nhwc"][0]), oracle.filtered_gelu(host(want), k.numpy(), k.numpy())) <= 2e-5
+    assert relmax(host(outs["nhwc"][0]), host(outs["nchw"][0])) <= 5e-6
+    assert relmax(host(outs["nhwc"][1]), host(outs["nchw"][1])) <= 2e-6
+    for a_, b_ in zip(outs["nhwc"][2] + outs["nhwc"][3], outs["nchw"][2] + outs["nchw"][3]):
+        assert relmax(host(a_), host(b_)) <= 2e-5
+
+
 def test_kernel_selection(afr):
     k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
     afr.filtered_gelu(torch.randn(2, 2, 32, 32, device="cuda"), k, k)
