@@ -390,11 +390,20 @@ def ddpm_v3(afr, ws, rank, global_batch, steps, warmup, schedule):
         state["i"] -= 1
 
     l0 = afr.launch_count()
-    eager_ms, _ = timed_loop(eager_step, steps, warmup, ws)
-    eager_ms /= steps
+    nchw_ms, _ = timed_loop(eager_step, steps, warmup, ws)
+    nchw_ms /= steps
     launches = (afr.launch_count() - l0) // (steps + warmup)
+    # the same model in channels-last memory: no cuDNN layout conversions, fused activations on fgelu3_nhwc_kernel
+    net = net.to(memory_format=torch.channels_last)
+    cl_ms, _ = timed_loop(eager_step, steps, warmup, ws)
+    cl_ms /= steps
+    use_cl = all_ok(cl_ms < nchw_ms, ws)
+    if not use_cl:
+        net = net.to(memory_format=torch.contiguous_format)
+    eager_ms = cl_ms if use_cl else nchw_ms
     out = {"global_batch": global_batch, "per_rank_batch": n, "schedule": schedule, "eager_ms_per_reverse_step": eager_ms,
-           "afr_launches_per_step": int(launches)}
+           "eager_ms_per_reverse_step_nchw": nchw_ms, "eager_ms_per_reverse_step_channels_last": cl_ms,
+           "memory_format": "channels_last" if use_cl else "nchw", "afr_launches_per_step": int(launches)}
     del x
     # the full run: graph captured once beforehand (reported separately), then ONE timed call
     mode = "cuda_graph"
@@ -443,7 +452,7 @@ def ddpm_v3(afr, ws, rank, global_batch, steps, warmup, schedule):
         try:
             rm = ref[2]
             rnet = rm.UNet(c_in=3, c_out=3, image_size=32, device="cuda", f_settings=FS, variant=3).cuda()
-            rnet.load_state_dict(net.state_dict(), strict=True)
+            rnet.load_state_dict({kk: vv.contiguous() for kk, vv in net.state_dict().items()}, strict=True)
             k = 3
             rdiff = rm.Diffusion(noise_steps=k + 1, img_size=32, device="cuda")
             import logging
@@ -461,7 +470,8 @@ def ddpm_v3(afr, ws, rank, global_batch, steps, warmup, schedule):
     else:
         out["reference_eager_ms_per_reverse_step"] = None
         out["reference_note"] = "no reference install (baseline/_ref) on this machine"
-    out["note"] = ("random-init UNet variant=3 c=3 32x32, fp32 (PyTorch default TF32 conv); samples/sec = global batch / wall time "
+    out["note"] = ("random-init UNet variant=3 c=3 32x32, fp32 (PyTorch default TF32 conv), model memory format = the faster of "
+                   "NCHW / channels-last on this shard (both eager figures reported); samples/sec = global batch / wall time "
                    "of ONE parallel.sharded_sample call (start noise from the seeded CPU draw + H2D, every reverse step, "
                    "snapshots every 100 steps, uint8 conversion, all-gather), max over ranks; strong scaling over ranks; "
                    "the reverse-step graph is captured before the timed call (graph_capture_s)")

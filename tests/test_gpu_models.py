@@ -255,6 +255,35 @@ def test_affine_kernel_vs_oracle(afr, oracle):
         afr.ops.filtered_gelu_affine(dev(x), dev(sc), dev(sh), oracle.lowpass_taps(1.0, 6, None), k)
 
 
+def test_unet_channels_last_matches_nchw(afr):
+    """The same Config-D UNet in channels-last memory (cuDNN then needs no nchw<->nhwc conversions and the fused
+    activations run through fgelu3_nhwc_kernel) gives the same output, input gradient and parameter gradients."""
+    g = golden("unet.npz")
+    tag = "v3_s32_c1"
+    res = {}
+    for fmt in ("nchw", "channels_last"):
+        net = fill_params_(afr.UNet(c_in=1, c_out=1, image_size=32, f_settings=FS, variant=3)).cuda()
+        if fmt == "channels_last":
+            net = net.to(memory_format=torch.channels_last)
+        x = dev(g[f"{tag}.x"], grad=True)
+        seen = []
+        hooks = [m.register_forward_hook(lambda mod, a, o: seen.append(afr.last_kernel()))
+                 for m in net.modules() if isinstance(m, afr.DoubleConv_F)]
+        y = net(x, dev(g[f"{tag}.t"]))
+        for h_ in hooks:
+            h_.remove()
+        y.square().mean().backward()
+        res[fmt] = (y.detach(), x.grad.clone(), torch.cat([p.grad.flatten() for p in net.parameters()]), seen)
+    assert relmax(host(res["channels_last"][0]), g[f"{tag}.y"]) <= UNET_TOL          # the reference's own output
+    # (in the NCHW model the bottleneck blocks see channels-last tensors too: SelfAttention's output is a
+    # channels-last strided view and convolutions keep their input's format -- they take the NHWC kernel as well)
+    assert set(res["channels_last"][3]) <= {"fgelu3_nhwc_kernel<sym>", "affine_apply_nhwc_kernel"}
+    assert "fgelu3_tma_kernel<sym>" in res["nchw"][3]
+    assert relmax(host(res["channels_last"][0]), host(res["nchw"][0])) <= 5e-5
+    assert relmax(host(res["channels_last"][1]), host(res["nchw"][1])) <= 2e-4
+    assert relmax(host(res["channels_last"][2]), host(res["nchw"][2])) <= 2e-4
+
+
 def test_param_count_v3(afr):
     # Results.ipynb:121 prints 5896513 for variant 3, c_in=1
     net = afr.UNet(c_in=1, c_out=1, image_size=32, f_settings=FS, variant=3)
