@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Compact timing table for A/B builds: fraction of the measured HBM peak per (op, shape, dtype).
-usage: [AFR_LIB_PATH=tools/variants/libafr_X.so] [AFR_...=..] python tools/ab_sweep.py [fused|resample|all] [tag]"""
+usage: [AFR_LIB_PATH=tools/variants/libafr_X.so] [AFR_...=..] python tools/ab_sweep.py [fused|resample|all|fused_cl] [tag]
+(fused_cl: the fused op on channels-last tensors)"""
 import json
 import os
 import sys
@@ -41,9 +42,11 @@ FUSED = [(256, 128, 64, 64), (1024, 64, 32, 32), (64, 64, 128, 128), (16, 64, 25
 RES = [(4096, 256, 4, 4), (4096, 128, 8, 8), (4096, 64, 16, 16), (2048, 32, 32, 32), (256, 128, 64, 64)]
 rows = []
 for dt, es, dn in ((torch.float32, 4, "f32"), (torch.bfloat16, 2, "bf16")):
-    if what in ("fused", "all"):
+    if what in ("fused", "all", "fused_cl"):
         for shp in FUSED:
             x = torch.randn(shp, device="cuda").to(dt); dy = torch.randn_like(x); n = x.numel()
+            if what == "fused_cl":
+                x = x.contiguous(memory_format=torch.channels_last); dy = dy.contiguous(memory_format=torch.channels_last)
             f = tm(lambda: afr.ops._fgelu_fwd(x, None, k, k)); kf = afr.last_kernel()
             b = tm(lambda: afr.ops._fgelu_bwd(x, None, dy, k, k))
             rows.append(("fgelu", shp, dn, 2 * n * es / f / 1e6 / PEAK, 3 * n * es / b / 1e6 / PEAK, kf))

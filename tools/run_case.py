@@ -16,6 +16,8 @@ NTAPS = int(os.environ.get("AFR_CASE_N", "3"))
 k = afr.Taps(afr.circularLowpassKernel(np.pi / 2, NTAPS, 2))
 x = torch.randn(B, C, H, W, device="cuda").to(dt)
 dy = torch.randn_like(x); r = torch.randn_like(x)
+if os.environ.get("AFR_CASE_CL") == "1":          # channels-last tensors (fgelu3_nhwc_kernel)
+    x, dy, r = (t.contiguous(memory_format=torch.channels_last) for t in (x, dy, r))
 big = torch.randn(B, C, 2 * H, 2 * W, device="cuda").to(dt) if op == "up_bwd" else None
 small = torch.randn(B, C, H // 2, W // 2, device="cuda").to(dt) if op == "down_bwd" else None
 fn = {"fgelu_fwd": lambda: afr.ops._fgelu_fwd(x, None, k, k), "fgelu_bwd": lambda: afr.ops._fgelu_bwd(x, None, dy, k, k),
