@@ -481,6 +481,29 @@ int afr_affine_apply_nhwc(const void *x, const float *scale_dev, const float *sh
                        "affine_apply_nhwc_kernel");
 }
 
+int afr_groupnorm1_bwd(const void *x, const void *dz, const float *gamma_dev, const float *mean_dev, const float *rstd_dev,
+                       void *dx, float *dgamma_dev, float *dbeta_dev, float *workspace_dev, int B, int C, int H, int W,
+                       int dtype, int channels_last, void *stream)
+{
+    if (B < 0 || C < 1 || H < 1 || W < 1) return fail(AFR_ERR_BAD_SHAPE, "bad shape");
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if (B == 0) return AFR_OK;
+    if (!x || !dz || !gamma_dev || !mean_dev || !rstd_dev || !dx || !dgamma_dev || !dbeta_dev || !workspace_dev)
+        return fail(AFR_ERR_NULL_POINTER, "NULL pointer");
+    const long hw = (long)H * W;
+    const bool ok_shape = channels_last ? (C % 32 == 0) : (hw % 4 == 0);
+    if (!ok_shape || (reinterpret_cast<uintptr_t>(x) % 16) || (reinterpret_cast<uintptr_t>(dz) % 16) ||
+        (reinterpret_cast<uintptr_t>(dx) % 16) || (reinterpret_cast<uintptr_t>(gamma_dev) % 16))
+        return fail(AFR_ERR_UNSUPPORTED, "GroupNorm backward needs H*W %% 4 == 0 (NCHW) or C %% 32 == 0 (channels-last) and "
+                                         "16-byte aligned buffers");
+    begin_call();
+    g_last_kernel = "gn_bwd_apply_kernel";
+    const int rc = cuda_status(groupnorm1_bwd(x, dz, gamma_dev, mean_dev, rstd_dev, dx, dgamma_dev, dbeta_dev, workspace_dev, B, C,
+                                              hw, dtype, channels_last != 0, (cudaStream_t)stream), "gn_bwd kernels");
+    if (rc == AFR_OK) g_launches.fetch_add(2, std::memory_order_relaxed);      // three kernels per call
+    return rc;
+}
+
 int afr_groupnorm1_stats(const void *x, const float *gamma_dev, const float *beta_dev, float eps, const float *add_dev,
                          float *scale_dev, float *shift_dev, float *mean_dev, float *rstd_dev, int B, int C, int H, int W,
                          int dtype, void *stream)

@@ -110,6 +110,10 @@ cudaError_t rotate_periodic_cubic(const float *x, float *y, long planes, int H, 
 cudaError_t groupnorm1_affine(const void *x, const float *gamma, const float *beta, float eps, float *scale,
                               float *shift, long B, int C, long hw, int dtype, cudaStream_t s, const float *add = nullptr,
                               float *mean_out = nullptr, float *rstd_out = nullptr);
+// afr_norm.cu -- GroupNorm(1, C) backward in three launches (workspace: 2*B*C + 2*B floats), NCHW or channels-last
+cudaError_t groupnorm1_bwd(const void *x, const void *dz, const float *gamma, const float *mean, const float *rstd, void *dx,
+                           float *dgamma, float *dbeta, float *workspace, long B, int C, long hw, int dtype, bool nhwc,
+                           cudaStream_t s);
 cudaError_t affine_apply(const void *x, const float *scale, const float *shift, void *y, long planes, long hw, int dtype,
                          cudaStream_t s);
 cudaError_t affine_apply_nhwc(const void *x, const float *scale, const float *shift, void *y, long B, int C, long hw, int dtype,

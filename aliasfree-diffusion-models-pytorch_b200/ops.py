@@ -8,6 +8,7 @@ Names mirror the reference: ``custom_upsample`` / ``custom_downsample`` have the
 signatures of modules/filtrs.py:79 and :71.
 """
 import ctypes
+import os
 
 import torch
 
@@ -465,11 +466,30 @@ def _gn_stats(h, weight, bias, eps, add=None):
     return scale, shift, mean, rstd
 
 
+# Our three-launch GroupNorm backward (csrc/afr_norm.cu) instead of ATen's; AFR_GN_BWD=aten switches back (A/B).
+USE_OWN_GN_BACKWARD = os.environ.get("AFR_GN_BWD", "afr") != "aten"
+
+
 def _gn_backward(dz, h, mean, rstd, weight):
-    """GroupNorm(1, C) backward (dz = gradient of the normalised + affine output): ATen's own kernels.  Called
-    directly, the ATen op reads its tensors as dense NCHW whatever their strides (measured: channels-last inputs give
-    dgamma / dbeta that are off by O(1)), so channels-last tensors are made NCHW-contiguous first."""
+    """GroupNorm(1, C) backward (dz = gradient of the normalised + affine output) -> (dh, dgamma, dbeta)."""
     B, C, H, W = h.shape
+    cl = _is_cl(h)
+    ok = (USE_OWN_GN_BACKWARD and h.dtype in _DT and weight.dtype == torch.float32 and weight.is_contiguous()
+          and ((cl and C % 32 == 0) or (not cl and h.is_contiguous() and (H * W) % 4 == 0)))
+    if ok:
+        dz = dz.to(h.dtype)
+        dz = dz.contiguous(memory_format=torch.channels_last) if cl else dz.contiguous()
+        dh = torch.empty_like(h)
+        dw = torch.empty(C, dtype=torch.float32, device=h.device)
+        db = torch.empty(C, dtype=torch.float32, device=h.device)
+        work = torch.empty(2 * B * C + 2 * B, dtype=torch.float32, device=h.device)
+        with _on_device(h.device):
+            _check(_native.lib().afr_groupnorm1_bwd(h.data_ptr(), dz.data_ptr(), weight.data_ptr(), mean.data_ptr(),
+                                                    rstd.data_ptr(), dh.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                                    work.data_ptr(), B, C, H, W, _DT[h.dtype], 1 if cl else 0, _stream(h)))
+        return dh, dw, db
+    # ATen's own kernels.  Called directly, the op reads its tensors as dense NCHW whatever their strides (measured:
+    # channels-last inputs give dgamma / dbeta that are off by O(1)), so they are made NCHW-contiguous first.
     return torch.ops.aten.native_group_norm_backward(dz.contiguous(), h.contiguous(), mean, rstd, weight, B, C, H * W, 1,
                                                      [True, True, True])
 

@@ -139,6 +139,17 @@ int afr_groupnorm1_stats(const void *x, const float *gamma_dev, const float *bet
                          const float *add_dev, float *scale_dev, float *shift_dev, float *mean_dev,
                          float *rstd_dev, int B, int C, int H, int W, int dtype, void *stream);
 
+/* Backward of GroupNorm(1, C) for the folded-norm training path: dz = gradient of the normalised + affine output
+ * (what afr_filtered_gelu_affine_bwd / ..._nhwc_bwd return, or the incoming gradient of afr_affine_apply), x the
+ * norm's input, mean_dev / rstd_dev from afr_groupnorm1_stats.  Writes dx (same layout as x), dgamma_dev and
+ * dbeta_dev (DEVICE fp32 [C]).  workspace_dev: DEVICE fp32 scratch of 2*B*C + 2*B elements owned by the caller.
+ * Three launches, deterministic (no atomics).  channels_last = 0: dense NCHW, H*W % 4 == 0; 1: channels-last memory,
+ * C % 32 == 0.  Replaces ATen's native_group_norm_backward on this path (modules/ddpm_utils.py:113, 116 under autograd). */
+int afr_groupnorm1_bwd(const void *x, const void *dz, const float *gamma_dev, const float *mean_dev,
+                       const float *rstd_dev, void *dx, float *dgamma_dev, float *dbeta_dev,
+                       float *workspace_dev, int B, int C, int H, int W, int dtype, int channels_last,
+                       void *stream);
+
 /* y = x * scale[b,c] + shift[b,c]: normalise + affine (+ the folded embedding) of a GroupNorm whose statistics came
  * from afr_groupnorm1_stats, as one pass (the reference runs GroupNorm, `.repeat` of the embedding and an add:
  * modules/ddpm_utils.py:385-387).  H*W must be a multiple of 4. */

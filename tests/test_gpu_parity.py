@@ -595,6 +595,41 @@ def test_channels_last_groupnorm_fold_and_embedding(afr, oracle):
         assert relmax(host(a_), host(b_)) <= 2e-5
 
 
+@pytest.mark.parametrize("fmt", ["nchw", "channels_last"])
+@pytest.mark.parametrize("shape", [(3, 32, 8, 8), (2, 64, 16, 12), (5, 96, 4, 4), (1, 32, 32, 32), (33, 32, 2, 4)])
+def test_groupnorm1_backward_kernels(afr, shape, fmt):
+    """afr_groupnorm1_bwd (three launches, both layouts) against autograd through F.group_norm in float64."""
+    from aliasfree_b200 import ops
+    B, C, H, W = shape
+    torch.manual_seed(C + H)
+    x = torch.randn(shape, device="cuda") * 1.5 + 0.3
+    dz = torch.randn(shape, device="cuda")
+    w = (1 + 0.2 * torch.randn(C, device="cuda")).requires_grad_(True)
+    b = (0.1 * torch.randn(C, device="cuda")).requires_grad_(True)
+    x64 = x.double().requires_grad_(True)
+    y = torch.nn.functional.group_norm(x64, 1, w.double(), b.double(), 1e-5)
+    gx, gw, gb = torch.autograd.grad(y, (x64, w, b), dz.double())
+    if fmt == "channels_last":
+        x, dz = x.contiguous(memory_format=torch.channels_last), dz.contiguous(memory_format=torch.channels_last)
+    _, _, mean, rstd = ops._gn_stats(x, w, b, 1e-5)
+    n0 = afr.launch_count()
+    dh, dw, db = ops._gn_backward(dz, x, mean, rstd, w.detach())
+    assert afr.launch_count() == n0 + 3 and afr.last_kernel() == "gn_bwd_apply_kernel"
+    assert dh.stride() == x.stride()
+    assert relmax(host(dh), gx.cpu().numpy()) <= 1e-5
+    assert relmax(host(dw), gw.double().cpu().numpy()) <= 1e-5
+    assert relmax(host(db), gb.double().cpu().numpy()) <= 1e-5
+    # bf16 storage, fp32 statistics and sums
+    xb, dzb = x.to(torch.bfloat16), dz.to(torch.bfloat16)
+    _, _, mean, rstd = ops._gn_stats(xb, w, b, 1e-5)
+    dhb, dwb, _ = ops._gn_backward(dzb, xb, mean, rstd, w.detach())
+    x64 = xb.double().contiguous().requires_grad_(True)
+    y = torch.nn.functional.group_norm(x64, 1, w.double(), b.double(), 1e-5)
+    gx, gw = torch.autograd.grad(y, (x64, w), dzb.double().contiguous())
+    assert dhb.dtype == torch.bfloat16 and relmax(host(dhb), gx.cpu().numpy()) <= BF16_TOL
+    assert relmax(host(dwb), gw.double().cpu().numpy()) <= 1e-4
+
+
 def test_kernel_selection(afr):
     k = afr.circularLowpassKernel(np.pi / 2, 3, 2)
     afr.filtered_gelu(torch.randn(2, 2, 32, 32, device="cuda"), k, k)
