@@ -523,28 +523,45 @@ def train_v3(afr, ws, rank, global_batch, steps, warmup):
     launches = (afr.launch_count() - l0) // (steps + warmup)
     eager_ms = total_ms / steps
     ms, mode = eager_ms, "eager"
-    gstep, timeline, opt_kind = None, None, "AdamW(foreach)"
-    try:                                   # same step, device work replayed from two CUDA graphs
-        try:                               # one multi-tensor kernel instead of ~36 foreach launches (same AdamW arithmetic)
-            opt_g = torch.optim.AdamW(net.parameters(), lr=3e-4, capturable=True, fused=True)
-            opt_kind = "AdamW(fused, capturable)"
-        except Exception:
-            opt_g = torch.optim.AdamW(net.parameters(), lr=3e-4, capturable=True)
-            opt_kind = "AdamW(foreach, capturable)"
-        gstep = parallel.GraphedTrainStep(net, diff, opt_g, tuple(dev.shape), ddp=ddp)
-    except Exception as e:
-        mode = "eager (graph capture failed: %s)" % repr(e)[:160]
-        gstep = None
-    if all_ok(gstep is not None, ws):
-        def graphed():
-            losses.append(gstep(host))
+    timeline, opt_kind, graph_ms, fmt_used = None, "AdamW(foreach)", {}, "nchw"
 
-        g_total, _ = timed_loop(graphed, steps, warmup, ws)
-        if g_total / steps < ms:
-            ms, mode = g_total / steps, "cuda_graph"
+    def make_graphed(model):
+        try:                               # one multi-tensor kernel instead of ~36 foreach launches (same AdamW arithmetic)
+            opt_g = torch.optim.AdamW(model.parameters(), lr=3e-4, capturable=True, fused=True)
+            kind = "AdamW(fused, capturable)"
+        except Exception:
+            opt_g = torch.optim.AdamW(model.parameters(), lr=3e-4, capturable=True)
+            kind = "AdamW(foreach, capturable)"
+        d = ddp if model is net else parallel.FlatGradAllReduce(model)
+        return parallel.GraphedTrainStep(model, diff, opt_g, tuple(dev.shape), ddp=d), kind, d
+
+    # the same step with its device work replayed from two CUDA graphs, with the model in NCHW and in channels-last
+    # memory (a copy with the same weights): large per-rank batches prefer NCHW, small ones channels-last
+    candidates = {}
+    for fmt in ("nchw", "channels_last"):
+        gs = None
+        try:
+            if fmt == "nchw":
+                model = net
+            else:
+                import copy
+                model = copy.deepcopy(net).to(memory_format=torch.channels_last)
+            gs, kind, d = make_graphed(model)
+        except Exception as e:
+            if fmt == "nchw":
+                mode = "eager (graph capture failed: %s)" % repr(e)[:160]
+        if all_ok(gs is not None, ws):
+            g_total, _ = timed_loop(lambda: losses.append(gs(host)), steps, warmup, ws)
+            graph_ms[fmt] = g_total / steps
+            candidates[fmt] = (gs, kind, d)
+    if graph_ms:
+        fmt_used = min(graph_ms, key=graph_ms.get)
+        gstep, opt_kind, ddp_used = candidates[fmt_used]
+        if graph_ms[fmt_used] < ms:
+            ms, mode = graph_ms[fmt_used], "cuda_graph"
         gstep.timeline = []                # a second, instrumented pass: where the step's device time goes
         for _ in range(steps):
-            graphed()
+            losses.append(gstep(host))
         timeline = gstep.timeline_ms()
         gstep.timeline = None
         t = time.perf_counter()
@@ -552,7 +569,8 @@ def train_v3(afr, ws, rank, global_batch, steps, warmup):
             diff.sample_timesteps(hi - lo)
         timeline["host_randint_ms"] = 1e3 * (time.perf_counter() - t) / steps
         timeline["sum_ms"] = sum(timeline[k] for k in ("inputs_h2d", "graph_fwd_bwd", "grad_allreduce", "graph_adamw"))
-        timeline["allreduce_bytes"] = int(ddp.flat.numel() * 4) if ws > 1 else 0
+        timeline["allreduce_bytes"] = int(ddp_used.flat.numel() * 4) if ws > 1 else 0
+    candidates.clear()
     # the unmodified reference's train step on this GPU (its UNet, its Diffusion, the lines of train())
     ref_ms, ref_note = None, "no reference install (baseline/_ref) on this machine"
     ref = load_reference()
@@ -586,6 +604,7 @@ def train_v3(afr, ws, rank, global_batch, steps, warmup):
             "global_batch": global_batch, "per_rank_batch": hi - lo, "steps_timed": steps,
             "final_loss": float(losses[-1].item()), "afr_launches_per_step": int(launches),
             "params": sum(p.numel() for p in net.parameters()), "timeline_ms": timeline, "optimizer": opt_kind,
+            "memory_format": fmt_used, "graph_ms_per_step_by_format": graph_ms,
             "reference_eager_ms_per_step": ref_ms, "speedup_vs_reference_eager": (ref_ms / ms) if ref_ms else None,
             "reference_note": ref_note,
             "note": "variant=3 c=3 32x32 fp32, AdamW lr 3e-4, H2D of the batch and one flat-gradient NCCL all-reduce per step"}
