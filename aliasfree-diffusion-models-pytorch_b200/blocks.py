@@ -129,6 +129,8 @@ class DoubleConv_F(nn.Module):
             if FUSE_GROUPNORM and ops.norm_fusable(h, self.norm2) and emb.dtype == h.dtype:
                 return ops.norm_add_emb(h, self.norm2, emb)
             return self.norm2(h) + emb[:, :, None, None]
+        if FUSE_GROUPNORM and ops.norm_fusable(h, self.norm2):
+            return ops.groupnorm1(h, self.norm2)                  # same values; keeps h's memory format
         return self.norm2(h)
 
 

@@ -551,7 +551,8 @@ class _NormFilteredGelu(torch.autograd.Function):
 
 
 class _NormAddEmb(torch.autograd.Function):
-    """GroupNorm(1, C)(h) + emb[:, :, None, None] as statistics kernel + ONE apply pass (emb folded into the shift)."""
+    """GroupNorm(1, C)(h) + emb[:, :, None, None] as statistics kernel + ONE apply pass (emb folded into the shift;
+    emb may be None: a plain GroupNorm in the tensor's own memory format with the three-launch backward)."""
 
     @staticmethod
     def run(h, weight, bias, eps, emb):
@@ -570,7 +571,7 @@ class _NormAddEmb(torch.autograd.Function):
     def forward(ctx, h, weight, bias, eps, emb):
         y, mean, rstd = _NormAddEmb.run(h, weight, bias, eps, emb)
         ctx.save_for_backward(h, weight, mean, rstd)
-        ctx.emb_dtype = emb.dtype
+        ctx.emb_dtype = None if emb is None else emb.dtype
         return y
 
     @staticmethod
@@ -579,7 +580,7 @@ class _NormAddEmb(torch.autograd.Function):
         h, weight, mean, rstd = ctx.saved_tensors
         dy = dy.contiguous()
         dh, dw, db = _gn_backward(dy, h, mean, rstd, weight)
-        return dh, dw, db, None, dy.sum(dim=(2, 3)).to(ctx.emb_dtype)
+        return dh, dw, db, None, (None if ctx.emb_dtype is None else dy.sum(dim=(2, 3)).to(ctx.emb_dtype))
 
 
 def norm_fusable(h, norm, n_up=3, n_down=3):
@@ -617,6 +618,16 @@ def norm_add_emb(h, norm, emb):
     if not _needs_grad(h, emb, norm.weight, norm.bias):
         return _NormAddEmb.run(h, norm.weight, norm.bias, norm.eps, emb)[0]
     return _NormAddEmb.apply(h, norm.weight, norm.bias, norm.eps, emb)
+
+
+def groupnorm1(h, norm):
+    """``norm(h)`` for a ``GroupNorm(1, C)`` module through the statistics + apply kernels and the three-launch
+    backward: same values as ``nn.GroupNorm``, but it keeps a channels-last tensor channels-last (ATen's GroupNorm
+    returns NCHW) and costs fewer launches.  Check ``norm_fusable`` first."""
+    h = _require(h, "h", keep_cl=True)
+    if not _needs_grad(h, norm.weight, norm.bias):
+        return _NormAddEmb.run(h, norm.weight, norm.bias, norm.eps, None)[0]
+    return _NormAddEmb.apply(h, norm.weight, norm.bias, norm.eps, None)
 
 
 def custom_upsample(x, sinc_filter, factor=2):
