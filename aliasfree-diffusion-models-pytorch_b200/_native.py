@@ -9,7 +9,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libafr_b200.so")
-SOURCES = ["afr_api.cu", "afr_generic.cu", "afr_n3.cu", "afr_stripn.cu", "afr_rotate.cu", "afr_small.cu", "afr_actdown.cu", "afr_norm.cu"]
+SOURCES = ["afr_api.cu", "afr_generic.cu", "afr_n3.cu", "afr_stripn.cu", "afr_rotate.cu", "afr_small.cu", "afr_actdown.cu", "afr_norm.cu", "afr_nhwc_resample.cu"]
 HEADERS = ["afr_common.cuh", "afr_kernels.h", os.path.join("..", "..", "include", "afr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "--threads", "0"]
@@ -77,6 +77,8 @@ def _declare(L):
     L.afr_filtered_gelu_nhwc_fwd.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
     L.afr_filtered_gelu_nhwc_bwd.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
     L.afr_affine_apply_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    L.afr_up2x_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, i64, i64, vp, ci, ci, ci, ci, vp]
+    L.afr_down2x_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, i64, i64, vp, ci, ci, ci, vp]
     L.afr_groupnorm1_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
     L.afr_filtered_gelu_bwd.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp]
     L.afr_gelu_down2x_fwd.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, ci, vp]
@@ -88,7 +90,8 @@ def _declare(L):
               "afr_filtered_gelu_fwd", "afr_filtered_gelu_bwd", "afr_filtered_gelu_affine_fwd", "afr_groupnorm1_affine",
               "afr_rotate_periodic_cubic", "afr_ddpm_update", "afr_ddpm_update_table", "afr_gelu_down2x_fwd",
               "afr_gelu_down2x_bwd", "afr_filtered_gelu_affine_bwd", "afr_groupnorm1_stats", "afr_affine_apply",
-              "afr_filtered_gelu_nhwc_fwd", "afr_filtered_gelu_nhwc_bwd", "afr_affine_apply_nhwc", "afr_groupnorm1_bwd"):
+              "afr_filtered_gelu_nhwc_fwd", "afr_filtered_gelu_nhwc_bwd", "afr_affine_apply_nhwc", "afr_groupnorm1_bwd",
+              "afr_up2x_nhwc", "afr_down2x_nhwc"):
         getattr(L, n).restype = ci
     return L
 
@@ -99,7 +102,8 @@ EXPORTS = ("afr_version", "afr_last_error", "afr_status_string", "afr_set_path",
            "afr_filtered_gelu_fwd", "afr_filtered_gelu_bwd", "afr_filtered_gelu_affine_fwd", "afr_groupnorm1_affine",
            "afr_rotate_periodic_cubic", "afr_ddpm_update", "afr_ddpm_update_table", "afr_gelu_down2x_fwd",
            "afr_gelu_down2x_bwd", "afr_filtered_gelu_affine_bwd", "afr_groupnorm1_stats", "afr_affine_apply",
-           "afr_filtered_gelu_nhwc_fwd", "afr_filtered_gelu_nhwc_bwd", "afr_affine_apply_nhwc", "afr_groupnorm1_bwd")
+           "afr_filtered_gelu_nhwc_fwd", "afr_filtered_gelu_nhwc_bwd", "afr_affine_apply_nhwc", "afr_groupnorm1_bwd",
+           "afr_up2x_nhwc", "afr_down2x_nhwc")
 
 
 def lib():

@@ -481,6 +481,40 @@ int afr_affine_apply_nhwc(const void *x, const float *scale_dev, const float *sh
                        "affine_apply_nhwc_kernel");
 }
 
+int afr_up2x_nhwc(const void *x, void *u, int B, int C, int H, int W, int64_t x_pixel_stride, int64_t u_pixel_stride,
+                  const float *taps, int N, int adjoint_of_down, int in_dtype, int out_dtype, void *stream)
+{
+    if (int rc = check_common(B, C, H, W, taps, N)) return rc;
+    if (!dtype_ok(in_dtype) || !dtype_ok(out_dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if ((long)B * C == 0) return AFR_OK;
+    if (!x || !u) return fail(AFR_ERR_NULL_POINTER, "x or u is NULL");
+    begin_call();
+    if (N != 3 || current_path() == AFR_PATH_GENERIC ||
+        !nhwc_resample_supported(C, x, u, (long)x_pixel_stride, (long)u_pixel_stride, in_dtype, out_dtype))
+        return fail(AFR_ERR_UNSUPPORTED, "channels-last up2x needs a 3x3 filter, C %% 4 == 0 and 4-element aligned bases / pixel strides");
+    Taps3 k; set_taps3(k, taps, adjoint_of_down != 0);
+    g_last_kernel = "up3_nhwc_kernel";
+    return cuda_status(nhwc_up_like(x, u, B, C, H, W, (long)x_pixel_stride, (long)u_pixel_stride, k, in_dtype, out_dtype,
+                                    (cudaStream_t)stream), "up3_nhwc_kernel");
+}
+
+int afr_down2x_nhwc(const void *v, void *y, int B, int C, int H, int W, int64_t v_pixel_stride, int64_t y_pixel_stride,
+                    const float *taps, int N, int adjoint_of_up, int dtype, void *stream)
+{
+    if (int rc = check_common(B, C, H, W, taps, N)) return rc;
+    if (!dtype_ok(dtype)) return fail(AFR_ERR_BAD_DTYPE, "bad dtype");
+    if ((long)B * C == 0) return AFR_OK;
+    if (!v || !y) return fail(AFR_ERR_NULL_POINTER, "v or y is NULL");
+    begin_call();
+    if (N != 3 || current_path() == AFR_PATH_GENERIC ||
+        !nhwc_resample_supported(C, v, y, (long)v_pixel_stride, (long)y_pixel_stride, dtype, dtype))
+        return fail(AFR_ERR_UNSUPPORTED, "channels-last down2x needs a 3x3 filter, C %% 4 == 0 and 4-element aligned bases / pixel strides");
+    Taps3 k; set_taps3(k, taps, adjoint_of_up != 0);
+    g_last_kernel = "down3_nhwc_kernel";
+    return cuda_status(nhwc_down_like(v, y, B, C, H, W, (long)v_pixel_stride, (long)y_pixel_stride, k, dtype, (cudaStream_t)stream),
+                       "down3_nhwc_kernel");
+}
+
 int afr_groupnorm1_bwd(const void *x, const void *dz, const float *gamma_dev, const float *mean_dev, const float *rstd_dev,
                        void *dx, float *dgamma_dev, float *dbeta_dev, float *workspace_dev, int B, int C, int H, int W,
                        int dtype, int channels_last, void *stream)

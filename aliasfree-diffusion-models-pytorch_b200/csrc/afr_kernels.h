@@ -97,6 +97,14 @@ bool flat_up_wanted(int H, int W, int in_dtype, int out_dtype);
 cudaError_t flat_up_like(const void *in, void *out, long planes, int C, long out_bstride, int H, int W, const Taps3 &k,
                          int in_dtype, int out_dtype, cudaStream_t s);
 
+// afr_nhwc_resample.cu -- N == 3 resamplers on channels-last memory; *ps = pixel stride in elements (C for a dense
+// tensor, the wider tensor's channel count for a channel slice)
+bool nhwc_resample_supported(int C, const void *a, const void *b, long aps, long bps, int adtype, int bdtype);
+cudaError_t nhwc_up_like(const void *x, void *u, long B, int C, int H, int W, long xps, long ups, const Taps3 &k, int in_dtype,
+                         int out_dtype, cudaStream_t s);
+cudaError_t nhwc_down_like(const void *v, void *y, long B, int C, int H, int W, long vps, long yps, const Taps3 &k, int dtype,
+                           cudaStream_t s);
+
 // afr_actdown.cu -- variant 4: gelu (+ GroupNorm affine) fused into the N == 3 downsampler, and its adjoint
 bool actdown_supported(int H, int W, const void *v, const void *y, int dtype);
 cudaError_t actdown_fwd(const void *v, const float *scale, const float *shift, void *y, long planes, int H, int W,

@@ -104,8 +104,33 @@ def _taps(filt):
 
 
 # ---- raw launches (no autograd) ---------------------------------------------------
+_CL = torch.channels_last
+
+
+def _cl_resample_ok(x, k):
+    """Channels-last tensors the NHWC resamplers take as they are (csrc/afr_nhwc_resample.cu)."""
+    return _is_cl(x) and k.n == 3 and x.shape[1] % 4 == 0 and x.dtype in _DT
+
+
+def _up_nhwc(x, u, k, adjoint, B, C, H, W, xps, ups):
+    with _on_device(x.device):
+        _check(_native.lib().afr_up2x_nhwc(x.data_ptr(), u.data_ptr(), B, C, H, W, xps, ups, k.ptr, k.n, 1 if adjoint else 0,
+                                           _DT[x.dtype], _DT[u.dtype], _stream(x)))
+
+
+def _down_nhwc(v, y, k, adjoint, B, C, H, W, vps, yps):
+    with _on_device(v.device):
+        _check(_native.lib().afr_down2x_nhwc(v.data_ptr(), y.data_ptr(), B, C, H, W, vps, yps, k.ptr, k.n, 1 if adjoint else 0,
+                                             _DT[v.dtype], _stream(v)))
+
+
 def _up_fwd(x, k, out_dtype):
     B, C, H, W = x.shape
+    if _cl_resample_ok(x, k):
+        u = torch.empty((B, C, 2 * H, 2 * W), dtype=out_dtype, device=x.device, memory_format=_CL)
+        _up_nhwc(x, u, k, False, B, C, H, W, C, C)
+        return u
+    x = x.contiguous()
     u = torch.empty((B, C, 2 * H, 2 * W), dtype=out_dtype, device=x.device)
     with _on_device(x.device):
         _check(_native.lib().afr_up2x_fwd(x.data_ptr(), u.data_ptr(), B, C, H, W, k.ptr, k.n,
@@ -115,6 +140,11 @@ def _up_fwd(x, k, out_dtype):
 
 def _up_bwd(du, k, H, W):
     B, C = du.shape[:2]
+    if _cl_resample_ok(du, k):
+        dx = torch.empty((B, C, H, W), dtype=du.dtype, device=du.device, memory_format=_CL)
+        _down_nhwc(du, dx, k, True, B, C, 2 * H, 2 * W, C, C)
+        return dx
+    du = du.contiguous()
     dx = torch.empty((B, C, H, W), dtype=du.dtype, device=du.device)
     with _on_device(du.device):
         _check(_native.lib().afr_up2x_bwd(du.data_ptr(), dx.data_ptr(), B, C, H, W, k.ptr, k.n,
@@ -124,6 +154,11 @@ def _up_bwd(du, k, H, W):
 
 def _down_fwd(v, k):
     B, C, H, W = v.shape
+    if _cl_resample_ok(v, k):
+        y = torch.empty((B, C, (H + 1) // 2, (W + 1) // 2), dtype=v.dtype, device=v.device, memory_format=_CL)
+        _down_nhwc(v, y, k, False, B, C, H, W, C, C)
+        return y
+    v = v.contiguous()
     y = torch.empty((B, C, (H + 1) // 2, (W + 1) // 2), dtype=v.dtype, device=v.device)
     with _on_device(v.device):
         _check(_native.lib().afr_down2x_fwd(v.data_ptr(), y.data_ptr(), B, C, H, W, k.ptr, k.n,
@@ -133,6 +168,11 @@ def _down_fwd(v, k):
 
 def _down_bwd(dy, k, H, W):
     B, C = dy.shape[:2]
+    if _cl_resample_ok(dy, k) and H % 2 == 0 and W % 2 == 0:
+        dv = torch.empty((B, C, H, W), dtype=dy.dtype, device=dy.device, memory_format=_CL)
+        _up_nhwc(dy, dv, k, True, B, C, H // 2, W // 2, C, C)
+        return dv
+    dy = dy.contiguous()
     dv = torch.empty((B, C, H, W), dtype=dy.dtype, device=dy.device)
     with _on_device(dy.device):
         _check(_native.lib().afr_down2x_bwd(dy.data_ptr(), dv.data_ptr(), B, C, H, W, k.ptr, k.n,
@@ -216,7 +256,7 @@ class _Up2x(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, du):
-        dx = _up_bwd(du.contiguous(), ctx.k, *ctx.hw)
+        dx = _up_bwd(du, ctx.k, *ctx.hw)
         return dx.to(ctx.in_dtype), None, None
 
 
@@ -229,7 +269,7 @@ class _Down2x(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
-        return _down_bwd(dy.contiguous(), ctx.k, *ctx.hw), None
+        return _down_bwd(dy, ctx.k, *ctx.hw), None
 
 
 class _FilteredGelu(torch.autograd.Function):
@@ -287,13 +327,46 @@ class _Up2xCat(torch.autograd.Function):
         return g[:, :ctx.cs], dx.to(ctx.in_dtype), None
 
 
+class _Up2xCatCL(torch.autograd.Function):
+    """The same on channels-last memory: the upsampler's channel slice of the concatenated tensor has pixel stride
+    Cs + C, which is all the NHWC kernels need."""
+
+    @staticmethod
+    def run(skip, x, k):
+        B, C, H, W = x.shape
+        Cs = skip.shape[1]
+        out = torch.empty((B, Cs + C, 2 * H, 2 * W), dtype=skip.dtype, device=skip.device, memory_format=_CL)
+        out[:, :Cs].copy_(skip)
+        _up_nhwc(x, out[:, Cs:], k, False, B, C, H, W, C, Cs + C)
+        return out
+
+    @staticmethod
+    def forward(ctx, skip, x, k):
+        ctx.k, ctx.shape, ctx.cs, ctx.in_dtype = k, tuple(x.shape), skip.shape[1], x.dtype
+        return _Up2xCatCL.run(skip, x, k)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        B, C, H, W = ctx.shape
+        g = g.contiguous(memory_format=_CL)
+        dx = torch.empty((B, C, H, W), dtype=g.dtype, device=g.device, memory_format=_CL)
+        _down_nhwc(g[:, ctx.cs:], dx, ctx.k, True, B, C, 2 * H, 2 * W, ctx.cs + C, C)
+        return g[:, :ctx.cs], dx.to(ctx.in_dtype), None
+
+
 def up2x_cat(skip, x, filt):
     """``torch.cat([skip, custom_upsample(x, filt)], dim=1)`` (modules/ddpm_utils.py:344-345, 413-414) without
     materialising the upsampled tensor separately: saves one read and one write of it.  Shapes the strided
     kernels do not cover (N != 3, W % 4 != 0, a forced kernel path) take the two-step form."""
-    x, skip = _require(x), _require(skip, "skip_x")
+    x, skip = _require(x, keep_cl=True), _require(skip, "skip_x", keep_cl=True)
     k = _taps(filt)
     B, C, H, W = x.shape
+    if (_is_cl(x) or _is_cl(skip)) and k.n == 3 and C % 4 == 0 and skip.shape[1] % 4 == 0 and skip.shape[0] == B \
+            and tuple(skip.shape[2:]) == (2 * H, 2 * W) and _native.lib().afr_set_path(-1) != _native.PATHS["generic"]:
+        x, skip = x.contiguous(memory_format=_CL), skip.contiguous(memory_format=_CL)
+        return _Up2xCatCL.apply(skip, x, k) if _needs_grad(skip, x) else _Up2xCatCL.run(skip, x, k)
+    x, skip = x.contiguous(), skip.contiguous()
     if (k.n == 3 and W % 4 == 0 and skip.shape[0] == B and tuple(skip.shape[2:]) == (2 * H, 2 * W)
             and (skip.shape[1] * 4 * H * W * skip.element_size()) % 32 == 0 and _native.PATHS_AUTO()):
         return _Up2xCat.apply(skip, x, k) if _needs_grad(skip, x) else _Up2xCat.run(skip, x, k)
@@ -315,15 +388,15 @@ def _match_residual(x, residual):
 # ---- public functions -----------------------------------------------------------------
 def up2x(x, filt, out_dtype=None):
     """Zero-stuff x2 + depthwise N x N low-pass, 'same' zero padding, no gain."""
-    x = _require(x)
+    x = _require(x, keep_cl=True)
     if not _needs_grad(x):
         return _up_fwd(x, _taps(filt), out_dtype or x.dtype)
     return _Up2x.apply(x, _taps(filt), out_dtype or x.dtype)
 
 
 def down2x(x, filt):
-    """Depthwise N x N low-pass then keep every 2nd row/column; output is contiguous."""
-    x = _require(x)
+    """Depthwise N x N low-pass then keep every 2nd row/column; output is dense (channels-last if x is)."""
+    x = _require(x, keep_cl=True)
     return _Down2x.apply(x, _taps(filt)) if _needs_grad(x) else _down_fwd(x, _taps(filt))
 
 

@@ -139,6 +139,21 @@ int afr_groupnorm1_stats(const void *x, const float *gamma_dev, const float *bet
                          const float *add_dev, float *scale_dev, float *shift_dev, float *mean_dev,
                          float *rstd_dev, int B, int C, int H, int W, int dtype, void *stream);
 
+/* custom_upsample / custom_downsample (and their adjoints) on channels-last memory, 3x3 filters, C % 4 == 0.
+ * afr_up2x_nhwc:   x [B,H,W,C] -> u [B,2H,2W,C]  (custom_upsample; with adjoint_of_down = 1 and the DOWN filter: the
+ *                  adjoint of custom_downsample for even H, W of its input, dy -> dv)
+ * afr_down2x_nhwc: v [B,H,W,C] -> y [B,ceil(H/2),ceil(W/2),C]  (custom_downsample; with adjoint_of_up = 1 and the UP filter:
+ *                  the adjoint of custom_upsample, du -> dx); H, W are the dims of v.
+ * `*_pixel_stride` = elements between consecutive pixels: C for a dense channels-last tensor, the channel count of the
+ * enclosing tensor when the operand is a channel slice -- custom_upsample writes straight into its half of the
+ * torch.cat buffer (modules/ddpm_utils.py:414) and its adjoint reads the gradient slice in place. */
+int afr_up2x_nhwc(const void *x, void *u, int B, int C, int H, int W, int64_t x_pixel_stride,
+                  int64_t u_pixel_stride, const float *taps, int N, int adjoint_of_down, int in_dtype,
+                  int out_dtype, void *stream);
+int afr_down2x_nhwc(const void *v, void *y, int B, int C, int H, int W, int64_t v_pixel_stride,
+                    int64_t y_pixel_stride, const float *taps, int N, int adjoint_of_up, int dtype,
+                    void *stream);
+
 /* Backward of GroupNorm(1, C) for the folded-norm training path: dz = gradient of the normalised + affine output
  * (what afr_filtered_gelu_affine_bwd / ..._nhwc_bwd return, or the incoming gradient of afr_affine_apply), x the
  * norm's input, mean_dev / rstd_dev from afr_groupnorm1_stats.  Writes dx (same layout as x), dgamma_dev and

@@ -557,6 +557,44 @@ def test_channels_last_fused_kernel(afr, oracle, shape, dtype):
     assert relmax(host(ya), oracle.filtered_gelu(x32, ka, kd)) <= tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 32, 16, 16), (3, 8, 5, 7), (1, 128, 4, 4), (2, 64, 8, 8), (5, 4, 1, 3), (1, 12, 32, 20)])
+def test_channels_last_resamplers(afr, oracle, shape, dtype):
+    """custom_upsample / custom_downsample, their adjoints and the concat write-through on channels-last tensors
+    (up3_nhwc_kernel / down3_nhwc_kernel): no layout copy, outputs stay channels-last, odd sizes included."""
+    B, C, H, W = shape
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    cl = torch.channels_last
+    rng = np.random.default_rng(C * 3 + H + W)
+    k = (oracle.lowpass_taps(np.pi / 2, 3, 2.0) + 0.03 * rng.standard_normal((3, 3))).astype(np.float32)
+    x = dev(rng.standard_normal(shape).astype(np.float32), dtype).contiguous(memory_format=cl)
+    if not afr.ops._is_cl(x):
+        pytest.skip("degenerate shape: channels-last == NCHW")
+    x32 = host(x)
+    xt = x.clone(memory_format=cl).requires_grad_(True)
+    u = afr.up2x(xt, k)
+    assert afr.last_kernel() == "up3_nhwc_kernel" and u.is_contiguous(memory_format=cl)
+    assert relmax(host(u), oracle.up2x(x32, k)) <= tol
+    du = dev(rng.standard_normal(tuple(u.shape)).astype(np.float32), dtype).contiguous(memory_format=cl)
+    (gx,) = torch.autograd.grad(u, xt, du)
+    assert relmax(host(gx), oracle.up2x_bwd(host(du), k)) <= tol
+    d = afr.down2x(xt, k)
+    assert afr.last_kernel() == "down3_nhwc_kernel" and tuple(d.shape) == (B, C, (H + 1) // 2, (W + 1) // 2)
+    assert relmax(host(d), oracle.down2x(x32, k)) <= tol
+    dd = dev(rng.standard_normal(tuple(d.shape)).astype(np.float32), dtype).contiguous(memory_format=cl)
+    (gx,) = torch.autograd.grad(d, xt, dd)
+    assert relmax(host(gx), oracle.down2x_bwd(host(dd), k, H, W)) <= tol
+    # concat write-through: skip channels are copied, the upsampler writes its slice (pixel stride Cs + C) in place
+    cs = 8
+    skip = dev(rng.standard_normal((B, cs, 2 * H, 2 * W)).astype(np.float32), dtype).contiguous(memory_format=cl).requires_grad_(True)
+    out = afr.up2x_cat(skip, xt, k)
+    assert afr.last_kernel() == "up3_nhwc_kernel" and out.is_contiguous(memory_format=cl)
+    assert torch.equal(out[:, :cs], skip) and relmax(host(out[:, cs:]), oracle.up2x(x32, k)) <= tol
+    g = dev(rng.standard_normal(tuple(out.shape)).astype(np.float32), dtype)
+    gs, gx = torch.autograd.grad(out, (skip, xt), g)
+    assert torch.equal(gs, g[:, :cs]) and relmax(host(gx), oracle.up2x_bwd(host(g[:, cs:]), k)) <= tol
+
+
 def test_channels_last_groupnorm_fold_and_embedding(afr, oracle):
     """The GroupNorm fold and the embedding fold on channels-last tensors: same values and gradients as the NCHW path."""
     from aliasfree_b200 import ops
