@@ -3,15 +3,20 @@
 // In a channels-last UNet the six custom_upsample / custom_downsample sites (and the torch.cat that follows an
 // upsample) were the last places that forced NCHW copies: ~40 direct_copy launches and 5 % of a reverse step at 4096
 // images (profiles/r02_ncu_launches_ddpm_step_b4096_channels_last.md).  These kernels take the tensors as they are.
-// "Flat" formulation (no row loop, every load issued up front, parallelism from the grid): a thread owns 4 channels
-// (one 128-bit vector) of
+// "Flat" formulation (no row loop over the plane, parallelism from the grid): a thread owns V channels (one 128-bit
+// vector: 4 fp32 or, when C % 8 == 0, 8 bf16) of
 //   up-like    one INPUT pixel (i, j): loads x[i][j], x[i][j+1], x[i+1][j], x[i+1][j+1] and writes the 2 x 2 output
 //              block (2i..2i+1, 2j..2j+1) -- consecutive lanes are consecutive channel groups, so every access of a
 //              warp is one or more whole 128-byte lines;
-//   down-like  one OUTPUT pixel (i, j): loads the 3 x 3 input neighbourhood of (2i, 2j) and writes one vector.
+//   down-like  a PH x PW block of OUTPUT pixels: walks the (2 PH + 1) x (2 PW + 1) input neighbourhood row by row
+//              (2 x 2 outputs: 25 loads for 4 outputs instead of 36, and 1.3x instead of 1.6x the input through L2).
+// The flat index is decomposed with multiply-high divisions (host-made magic numbers): three runtime integer
+// divisions were a fifth of the 1 x 1 kernel's instructions.
 // Either side may be a channel slice of a wider tensor (pixel stride > C): custom_upsample writes straight into its
 // half of the concatenated tensor and its adjoint reads the gradient slice in place.  `taps` arrive already arranged
 // for the stencil (flipped for the adjoints, see afr_api.cu).
+#include <cstdlib>
+
 #include "afr_common.cuh"
 #include "afr_kernels.h"
 
@@ -19,73 +24,160 @@ namespace afr {
 
 namespace {
 
-template <typename T> __device__ __forceinline__ float4 ldc4(const T *p);
-template <> __device__ __forceinline__ float4 ldc4<float>(const float *p) { return ld4(p); }
-template <> __device__ __forceinline__ float4 ldc4<bf16>(const bf16 *p) { return ld4(p); }
+// n / d for n < 2^31: umulhi(n, m) >> s with m = ceil(2^(31 + ceil(log2 d)) / d)
+struct FastDiv {
+    unsigned m, s, d;
+};
 
-__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-__device__ __forceinline__ float4 f4mul(float k, float4 a) { return make_float4(k * a.x, k * a.y, k * a.z, k * a.w); }
-__device__ __forceinline__ float4 f4fma(float k, float4 a, float4 c)
+FastDiv make_fastdiv(unsigned d)
 {
-    return make_float4(fmaf(k, a.x, c.x), fmaf(k, a.y, c.y), fmaf(k, a.z, c.z), fmaf(k, a.w, c.w));
+    FastDiv f{0u, 0u, d};
+    if (d > 1) {
+        unsigned l = 0;
+        while ((1ull << l) < d) ++l;
+        const unsigned p = 31 + l;
+        f.m = (unsigned)(((1ull << p) + d - 1) / d);
+        f.s = p - 32;
+    }
+    return f;
 }
 
-// x: [B, H, W, (xps)] -> u: [B, 2H, 2W, (ups)], C4 = C / 4 channel vectors per pixel
-template <typename TI, typename TO>
+__device__ __forceinline__ unsigned fdiv(unsigned n, const FastDiv &f) { return f.d == 1 ? n : (__umulhi(n, f.m) >> f.s); }
+
+template <int V, typename T> __device__ __forceinline__ void ldv(const T *p, float (&v)[V])
+{
+    if constexpr (V == 8) {
+        ld8(p, v);
+    } else {
+        const float4 a = ld4(p);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+}
+template <int V, typename T> __device__ __forceinline__ void ldv_if(bool ok, const T *p, float (&v)[V])
+{
+    if (ok) {
+        ldv<V>(p, v);
+    } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = 0.f;
+    }
+}
+template <int V, typename T> __device__ __forceinline__ void stv(T *p, const float (&v)[V])
+{
+    if constexpr (V == 8) st8(p, v);
+    else st4(p, make_float4(v[0], v[1], v[2], v[3]));
+}
+
+// x: [B, H, W, (xps)] -> u: [B, 2H, 2W, (ups)], C / V channel vectors per pixel
+template <typename TI, typename TO, int V>
 __global__ void __launch_bounds__(256)
-up3_nhwc_kernel(const TI *__restrict__ x, TO *__restrict__ u, unsigned total, int C4, int H, int W, long xps, long ups,
-                const __grid_constant__ Taps3 k)
+up3_nhwc_kernel(const TI *__restrict__ x, TO *__restrict__ u, unsigned total, FastDiv dCV, FastDiv dW, FastDiv dH, int H, int W,
+                long xps, long ups, const __grid_constant__ Taps3 k)
 {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const unsigned pix = idx / (unsigned)C4;
-    const int c = 4 * (int)(idx - pix * (unsigned)C4);
-    const unsigned row = pix / (unsigned)W;                      // b * H + i
-    const int j = (int)(pix - row * (unsigned)W);
-    const int i = (int)(row % (unsigned)H);
+    const unsigned pix = fdiv(idx, dCV);
+    const int c = V * (int)(idx - pix * dCV.d);
+    const unsigned row = fdiv(pix, dW);                          // b * H + i
+    const int j = (int)(pix - row * dW.d);
+    const unsigned b = fdiv(row, dH);
+    const int i = (int)(row - b * dH.d);
     const bool has_r = j + 1 < W, has_b = i + 1 < H;
     const TI *p = x + (long)pix * xps + c;
-    const float4 a = ldc4<TI>(p);
-    const float4 ar = has_r ? ldc4<TI>(p + xps) : f4zero();
-    const float4 ab = has_b ? ldc4<TI>(p + (long)W * xps) : f4zero();
-    const float4 abr = (has_r && has_b) ? ldc4<TI>(p + (long)(W + 1) * xps) : f4zero();
-    const unsigned b = row / (unsigned)H;
-    TO *o = u + (((long)b * 2 * H + 2 * i) * (2L * W) + 2 * j) * ups + c;
+    float a[V], ar[V], ab[V], abr[V], o[V];
+    ldv<V>(p, a);
+    ldv_if<V>(has_r, p + xps, ar);
+    ldv_if<V>(has_b, p + (long)W * xps, ab);
+    ldv_if<V>(has_r && has_b, p + (long)(W + 1) * xps, abr);
+    TO *q = u + (((long)b * 2 * H + 2 * i) * (2L * W) + 2 * j) * ups + c;
     const long orow = 2L * W * ups;
-    st4(o, f4mul(k.k[1][1], a));                                                        // (2i,   2j)
-    st4(o + ups, f4fma(k.k[1][2], ar, f4mul(k.k[1][0], a)));                            // (2i,   2j+1)
-    st4(o + orow, f4fma(k.k[2][1], ab, f4mul(k.k[0][1], a)));                           // (2i+1, 2j)
-    st4(o + orow + ups, f4fma(k.k[2][2], abr, f4fma(k.k[2][0], ab, f4fma(k.k[0][2], ar, f4mul(k.k[0][0], a)))));
+#pragma unroll
+    for (int e = 0; e < V; ++e) o[e] = k.k[1][1] * a[e];
+    stv<V>(q, o);                                                                        // (2i,   2j)
+#pragma unroll
+    for (int e = 0; e < V; ++e) o[e] = fmaf(k.k[1][2], ar[e], k.k[1][0] * a[e]);
+    stv<V>(q + ups, o);                                                                  // (2i,   2j+1)
+#pragma unroll
+    for (int e = 0; e < V; ++e) o[e] = fmaf(k.k[2][1], ab[e], k.k[0][1] * a[e]);
+    stv<V>(q + orow, o);                                                                 // (2i+1, 2j)
+#pragma unroll
+    for (int e = 0; e < V; ++e) o[e] = fmaf(k.k[2][2], abr[e], fmaf(k.k[2][0], ab[e], fmaf(k.k[0][2], ar[e], k.k[0][0] * a[e])));
+    stv<V>(q + orow + ups, o);                                                           // (2i+1, 2j+1)
 }
 
-// v: [B, H, W, (vps)] -> y: [B, Ho, Wo, (yps)], Ho = ceil(H / 2), Wo = ceil(W / 2)
-template <typename T>
-__global__ void __launch_bounds__(256)
-down3_nhwc_kernel(const T *__restrict__ v, T *__restrict__ y, unsigned total, int C4, int H, int W, int Ho, int Wo, long vps,
-                  long yps, const __grid_constant__ Taps3 k)
+// v: [B, H, W, (vps)] -> y: [B, Ho, Wo, (yps)], Ho = ceil(H / 2), Wo = ceil(W / 2); a thread makes PH x PW outputs
+// Minimum CTAs per SM: 8 bf16 channels x 1 output at 5 (48 registers instead of 56: 0.72-0.86 of the HBM peak instead of
+// 0.68-0.80; 6 CTAs = 40 registers spills and drops to 0.54-0.69); 8 x 2 x 2 at 2 (128 registers).
+template <typename T, int V, int PH, int PW, int MINB = (V == 8 && PH * PW == 1) ? 5 : ((PH * PW * V >= 32) ? 2 : 1)>
+__global__ void __launch_bounds__(256, MINB)
+down3_nhwc_kernel(const T *__restrict__ v, T *__restrict__ y, unsigned total, FastDiv dCV, FastDiv dWb, FastDiv dHb, int H, int W,
+                  int Ho, int Wo, long vps, long yps, const __grid_constant__ Taps3 k)
 {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const unsigned pix = idx / (unsigned)C4;
-    const int c = 4 * (int)(idx - pix * (unsigned)C4);
-    const unsigned row = pix / (unsigned)Wo;                     // b * Ho + i
-    const int j = (int)(pix - row * (unsigned)Wo);
-    const unsigned b = row / (unsigned)Ho;
-    const int i = (int)(row - b * (unsigned)Ho);
-    const T *base = v + ((long)b * H * W) * vps + c;
-    float4 acc = f4zero();
+    const unsigned pb = fdiv(idx, dCV);
+    const int c = V * (int)(idx - pb * dCV.d);
+    const unsigned rowb = fdiv(pb, dWb);                         // b * Hb + ib
+    const int j0 = PW * (int)(pb - rowb * dWb.d);
+    const unsigned b = fdiv(rowb, dHb);
+    const int i0 = PH * (int)(rowb - b * dHb.d);
+    const T *base = v + ((long)b * H * W + (2 * j0 - 1)) * vps + c;
+    float acc[PH][PW][V];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const int r = 2 * i + a - 1;
-        if ((unsigned)r >= (unsigned)H) continue;
+    for (int a = 0; a < PH; ++a)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const int col = 2 * j + q - 1;
-            if ((unsigned)col >= (unsigned)W) continue;
-            acc = f4fma(k.k[a][q], ldc4<T>(base + ((long)r * W + col) * vps), acc);
+        for (int q = 0; q < PW; ++q)
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[a][q][e] = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 2 * PH + 1; ++rr) {
+        const int r = 2 * i0 - 1 + rr;
+        const bool row_ok = (unsigned)r < (unsigned)H;
+        const T *rp = base + (long)r * W * vps;
+        float in[2 * PW + 1][V];
+#pragma unroll
+        for (int cc = 0; cc < 2 * PW + 1; ++cc)
+            ldv_if<V>(row_ok && (unsigned)(2 * j0 - 1 + cc) < (unsigned)W, rp + cc * vps, in[cc]);
+#pragma unroll
+        for (int a = 0; a < PH; ++a) {
+            const int ta = rr - 2 * a;                           // tap row this input row meets in output row i0 + a
+            if (ta < 0 || ta > 2) continue;
+#pragma unroll
+            for (int q = 0; q < PW; ++q)
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+#pragma unroll
+                    for (int e = 0; e < V; ++e) acc[a][q][e] = fmaf(k.k[ta][t], in[2 * q + t][e], acc[a][q][e]);
         }
     }
-    st4(y + (long)pix * yps + c, acc);
+#pragma unroll
+    for (int a = 0; a < PH; ++a)
+#pragma unroll
+        for (int q = 0; q < PW; ++q)
+            if (i0 + a < Ho && j0 + q < Wo) stv<V>(y + ((((long)b * Ho + i0 + a) * Wo) + j0 + q) * yps + c, acc[a][q]);
+}
+
+bool vec8_ok(int C, const void *a, const void *b, long aps, long bps)
+{
+    static const bool off = [] { const char *e = getenv("AFR_NHWC_V8"); return e && e[0] == '0'; }();
+    return !off && (C % 8) == 0 && (aps % 8) == 0 && (bps % 8) == 0 && (reinterpret_cast<uintptr_t>(a) % 16) == 0 &&
+           (reinterpret_cast<uintptr_t>(b) % 16) == 0;
+}
+
+// outputs per thread of the down-like kernel: AFR_NHWC_DOWN = 11 | 12 | 21 | 22 (default: by size)
+int down_block_default(long outputs, int Ho, int Wo, bool is_bf16)
+{
+    // fp32: 2 x 2 outputs per thread (1.04-1.10 of the copy peak against 0.96-1.02) unless the tensor is tiny; bf16: the
+    // blocks need 77-128 registers with 8-channel vectors and lose more to occupancy than they save (0.43-0.60 vs 0.72-0.86;
+    // profiles/r02_nhwc_down_ab.txt)
+    return (!is_bf16 && Ho >= 2 && Wo >= 2 && outputs >= (1L << 20)) ? 22 : 11;
+}
+
+// read on every call: tests and tools/nhwc_down_ab.py switch it inside one process
+int down_block_override()
+{
+    const char *e = getenv("AFR_NHWC_DOWN");
+    return e ? atoi(e) : 0;
 }
 
 }  // namespace
@@ -100,14 +192,19 @@ bool nhwc_resample_supported(int C, const void *a, const void *b, long aps, long
 cudaError_t nhwc_up_like(const void *x, void *u, long B, int C, int H, int W, long xps, long ups, const Taps3 &k, int in_dtype,
                          int out_dtype, cudaStream_t s)
 {
-    const long total = B * H * W * (C / 4);
-    if (total >= 0xffffff00L) return cudaErrorInvalidConfiguration;
+    const bool v8 = in_dtype == AFR_BF16 && out_dtype == AFR_BF16 && vec8_ok(C, x, u, xps, ups);
+    const int CV = C / (v8 ? 8 : 4);
+    const long total = B * H * W * CV;
+    if (total >= 0x7fffff00L) return cudaErrorInvalidConfiguration;
     const unsigned grid = (unsigned)((total + 255) / 256);
-#define AFR_UN(TI, TO) up3_nhwc_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI *)x, (TO *)u, (unsigned)total, C / 4, H, W, xps, ups, k)
-    if (in_dtype == AFR_F32 && out_dtype == AFR_F32) AFR_UN(float, float);
-    else if (in_dtype == AFR_BF16 && out_dtype == AFR_BF16) AFR_UN(bf16, bf16);
-    else if (in_dtype == AFR_BF16 && out_dtype == AFR_F32) AFR_UN(bf16, float);
-    else AFR_UN(float, bf16);
+    const FastDiv dCV = make_fastdiv((unsigned)CV), dW = make_fastdiv((unsigned)W), dH = make_fastdiv((unsigned)H);
+#define AFR_UN(TI, TO, V) \
+    up3_nhwc_kernel<TI, TO, V><<<grid, 256, 0, s>>>((const TI *)x, (TO *)u, (unsigned)total, dCV, dW, dH, H, W, xps, ups, k)
+    if (v8) AFR_UN(bf16, bf16, 8);
+    else if (in_dtype == AFR_F32 && out_dtype == AFR_F32) AFR_UN(float, float, 4);
+    else if (in_dtype == AFR_BF16 && out_dtype == AFR_BF16) AFR_UN(bf16, bf16, 4);
+    else if (in_dtype == AFR_BF16 && out_dtype == AFR_F32) AFR_UN(bf16, float, 4);
+    else AFR_UN(float, bf16, 4);
 #undef AFR_UN
     return cudaGetLastError();
 }
@@ -116,13 +213,31 @@ cudaError_t nhwc_down_like(const void *v, void *y, long B, int C, int H, int W, 
                            cudaStream_t s)
 {
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-    const long total = B * Ho * Wo * (C / 4);
-    if (total >= 0xffffff00L) return cudaErrorInvalidConfiguration;
+    const bool v8 = dtype == AFR_BF16 && vec8_ok(C, v, y, vps, yps);
+    const int CV = C / (v8 ? 8 : 4);
+    int blk = down_block_override();
+    if (blk != 11 && blk != 12 && blk != 21 && blk != 22) blk = down_block_default(B * Ho * Wo * CV, Ho, Wo, dtype == AFR_BF16);
+    const int PH = blk / 10, PW = blk % 10;
+    const int Hb = (Ho + PH - 1) / PH, Wb = (Wo + PW - 1) / PW;
+    const long total = B * Hb * Wb * CV;
+    if (total >= 0x7fffff00L) return cudaErrorInvalidConfiguration;
     const unsigned grid = (unsigned)((total + 255) / 256);
-    if (dtype == AFR_F32)
-        down3_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float *)v, (float *)y, (unsigned)total, C / 4, H, W, Ho, Wo, vps, yps, k);
-    else
-        down3_nhwc_kernel<bf16><<<grid, 256, 0, s>>>((const bf16 *)v, (bf16 *)y, (unsigned)total, C / 4, H, W, Ho, Wo, vps, yps, k);
+    const FastDiv dCV = make_fastdiv((unsigned)CV), dWb = make_fastdiv((unsigned)Wb), dHb = make_fastdiv((unsigned)Hb);
+#define AFR_DN(T, V, PH_, PW_)                                                                                            \
+    down3_nhwc_kernel<T, V, PH_, PW_><<<grid, 256, 0, s>>>((const T *)v, (T *)y, (unsigned)total, dCV, dWb, dHb, H, W, Ho, Wo, \
+                                                           vps, yps, k)
+#define AFR_DN_P(T, V)                                                                                                    \
+    do {                                                                                                                  \
+        if (blk == 22) AFR_DN(T, V, 2, 2);                                                                                \
+        else if (blk == 21) AFR_DN(T, V, 2, 1);                                                                           \
+        else if (blk == 12) AFR_DN(T, V, 1, 2);                                                                           \
+        else AFR_DN(T, V, 1, 1);                                                                                          \
+    } while (0)
+    if (dtype == AFR_F32) AFR_DN_P(float, 4);
+    else if (v8) AFR_DN_P(bf16, 8);
+    else AFR_DN_P(bf16, 4);
+#undef AFR_DN_P
+#undef AFR_DN
     return cudaGetLastError();
 }
 

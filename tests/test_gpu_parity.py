@@ -595,6 +595,38 @@ def test_channels_last_resamplers(afr, oracle, shape, dtype):
     assert torch.equal(gs, g[:, :cs]) and relmax(host(gx), oracle.up2x_bwd(host(g[:, cs:]), k)) <= tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("blk", ["11", "12", "21", "22"])
+@pytest.mark.parametrize("shape", [(2, 32, 16, 16), (3, 8, 5, 7), (2, 16, 7, 5), (1, 128, 4, 4), (5, 4, 1, 3), (3, 12, 3, 1),
+                                   (1, 24, 34, 18), (2, 8, 2, 2)])
+def test_channels_last_down_output_blocks(afr, oracle, monkeypatch, shape, blk, dtype):
+    """down3_nhwc_kernel with every outputs-per-thread block (1x1, 1x2, 2x1, 2x2; 8-channel vectors for bf16 when
+    C % 8 == 0): forward and the up-like adjoint's counterpart, odd sizes and one-pixel planes included."""
+    monkeypatch.setenv("AFR_NHWC_DOWN", blk)
+    B, C, H, W = shape
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    cl = torch.channels_last
+    rng = np.random.default_rng(C + 7 * H + W)
+    k = (oracle.lowpass_taps(np.pi / 2, 3, 2.0) + 0.03 * rng.standard_normal((3, 3))).astype(np.float32)
+    x = dev(rng.standard_normal(shape).astype(np.float32), dtype).contiguous(memory_format=cl)
+    if not afr.ops._is_cl(x):
+        pytest.skip("degenerate shape: channels-last == NCHW")
+    d = afr.ops._down_fwd(x, afr.Taps(k))
+    assert afr.last_kernel() == "down3_nhwc_kernel" and d.is_contiguous(memory_format=cl)
+    assert relmax(host(d), oracle.down2x(host(x), k)) <= tol
+    # the adjoint of up2x is down-like as well
+    g = dev(rng.standard_normal((B, C, 2 * H, 2 * W)).astype(np.float32), dtype).contiguous(memory_format=cl)
+    gx = afr.ops._up_bwd(g, afr.Taps(k), H, W)
+    assert afr.last_kernel() == "down3_nhwc_kernel"
+    assert relmax(host(gx), oracle.up2x_bwd(host(g), k)) <= tol
+    # a channel slice as the source (the gradient of the concat write-through)
+    for cs in (8, 4):                                    # 4: a bf16 slice that is only 8-byte aligned (4-channel vectors)
+        wide = dev(rng.standard_normal((B, cs + C, 2 * H, 2 * W)).astype(np.float32), dtype).contiguous(memory_format=cl)
+        gx = torch.empty((B, C, H, W), dtype=dtype, device="cuda").contiguous(memory_format=cl)
+        afr.ops._down_nhwc(wide[:, cs:], gx, afr.Taps(k), True, B, C, 2 * H, 2 * W, cs + C, C)
+        assert relmax(host(gx), oracle.up2x_bwd(host(wide[:, cs:]), k)) <= tol
+
+
 def test_channels_last_groupnorm_fold_and_embedding(afr, oracle):
     """The GroupNorm fold and the embedding fold on channels-last tensors: same values and gradients as the NCHW path."""
     from aliasfree_b200 import ops

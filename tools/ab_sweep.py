@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Compact timing table for A/B builds: fraction of the measured HBM peak per (op, shape, dtype).
-usage: [AFR_LIB_PATH=tools/variants/libafr_X.so] [AFR_...=..] python tools/ab_sweep.py [fused|resample|all|fused_cl] [tag]
-(fused_cl: the fused op on channels-last tensors)"""
+usage: [AFR_LIB_PATH=tools/variants/libafr_X.so] [AFR_...=..] python tools/ab_sweep.py [fused|resample|all|fused_cl|resample_cl] [tag]
+(fused_cl / resample_cl: the same ops on channels-last tensors)"""
 import json
 import os
 import sys
@@ -51,9 +51,11 @@ for dt, es, dn in ((torch.float32, 4, "f32"), (torch.bfloat16, 2, "bf16")):
             b = tm(lambda: afr.ops._fgelu_bwd(x, None, dy, k, k))
             rows.append(("fgelu", shp, dn, 2 * n * es / f / 1e6 / PEAK, 3 * n * es / b / 1e6 / PEAK, kf))
             del x, dy
-    if what in ("resample", "all"):
+    if what in ("resample", "all", "resample_cl"):
         for shp in RES:
             x = torch.randn(shp, device="cuda").to(dt); n = x.numel()
+            if what == "resample_cl":
+                x = x.contiguous(memory_format=torch.channels_last)
             u = tm(lambda: afr.ops._up_fwd(x, k, dt)); ku = afr.last_kernel()
             d = tm(lambda: afr.ops._down_fwd(x, k)); kd = afr.last_kernel()
             rows.append(("up/down", shp, dn, 5 * n * es / u / 1e6 / PEAK, 1.25 * n * es / d / 1e6 / PEAK, ku + " / " + kd))
