@@ -153,7 +153,9 @@ int afr_up2x_fwd(const void *x, void *u, int B, int C, int H, int W, const float
     begin_call();
     const int path = current_path();
     const bool small_up = N == 3 && path == AFR_PATH_AUTO && small_up_supported(H, W, x, u, 4L * H * W, out_dtype);
-    if (small_up && (warp_up_shape(H, W) || !n3_up_supported(H, W, x, u, in_dtype, out_dtype))) {
+    // fp32 outputs: the loop-free kernel with one float4 store per lane beats the warp-shuffle planes too
+    const bool flat_first = n3_up_supported(H, W, x, u, in_dtype, out_dtype) && flat_up_wanted(H, W, in_dtype, out_dtype);
+    if (small_up && !flat_first && (warp_up_shape(H, W) || !n3_up_supported(H, W, x, u, in_dtype, out_dtype))) {
         Taps3 k; set_taps3(k, taps, false);
         g_last_kernel = warp_up_shape(H, W) ? "up3_warp_kernel" : "up3_group_kernel";
         return cuda_status(small_up_like(x, u, planes, 1, 4L * H * W, H, W, k, in_dtype, out_dtype, s), g_last_kernel);
@@ -222,7 +224,8 @@ int afr_up2x_fwd_strided(const void *x, void *u, int B, int C, int H, int W, int
         return fail(AFR_ERR_UNSUPPORTED, "strided up2x needs N == 3 and the AUTO kernel path");
     Taps3 k; set_taps3(k, taps, false);
     const bool strip_ok = n3_up_supported(H, W, x, u, in_dtype, out_dtype) && (out_batch_stride % 8) == 0;
-    if (small_up_supported(H, W, x, u, (long)out_batch_stride, out_dtype) && (warp_up_shape(H, W) || !strip_ok)) {
+    const bool flat_first = strip_ok && flat_up_wanted(H, W, in_dtype, out_dtype);
+    if (!flat_first && small_up_supported(H, W, x, u, (long)out_batch_stride, out_dtype) && (warp_up_shape(H, W) || !strip_ok)) {
         g_last_kernel = warp_up_shape(H, W) ? "up3_warp_kernel" : "up3_group_kernel";
         return cuda_status(small_up_like(x, u, planes, C, (long)out_batch_stride, H, W, k, in_dtype, out_dtype,
                                          (cudaStream_t)stream), g_last_kernel);
@@ -308,7 +311,8 @@ int afr_down2x_bwd(const void *dy, void *dv, int B, int C, int H, int W, const f
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     const bool small_up = N == 3 && path == AFR_PATH_AUTO && (H % 2) == 0 && (W % 2) == 0 &&
                           small_up_supported(Ho, Wo, dy, dv, (long)H * W, dtype);
-    if (small_up && (warp_up_shape(Ho, Wo) || !n3_up_supported(Ho, Wo, dy, dv, dtype, dtype))) {
+    const bool flat_first = n3_up_supported(Ho, Wo, dy, dv, dtype, dtype) && flat_up_wanted(Ho, Wo, dtype, dtype);
+    if (small_up && !flat_first && (warp_up_shape(Ho, Wo) || !n3_up_supported(Ho, Wo, dy, dv, dtype, dtype))) {
         Taps3 k; set_taps3(k, taps, true);
         g_last_kernel = warp_up_shape(Ho, Wo) ? "up3_warp_kernel" : "up3_group_kernel";
         return cuda_status(small_up_like(dy, dv, planes, 1, (long)H * W, Ho, Wo, k, dtype, dtype, s), g_last_kernel);

@@ -1645,8 +1645,10 @@ cudaError_t n3_up_like(const void *in, void *out, long planes, int H, int W, con
                        int in_dtype, int out_dtype, cudaStream_t s, int C, long out_bstride)
 {
     if (planes > 0x7fffffffL) return cudaErrorInvalidConfiguration;
-    if (flat_up_wanted(H, W, in_dtype, out_dtype))
-        return flat_up_like(in, out, planes, C, out_bstride, H, W, k, in_dtype, out_dtype, s);
+    if (flat_up_wanted(H, W, in_dtype, out_dtype)) {
+        const cudaError_t e = flat_up_like(in, out, planes, C, out_bstride, H, W, k, in_dtype, out_dtype, s);
+        if (e != cudaErrorInvalidConfiguration) return e;        // more than 2^32 threads: the strips below take it
+    }
     const int strips = W / 4, R = pick_rows(H), nseg = (H + R - 1) / R;
     const long total = planes * (long)strips * nseg;
     const long grid = (total + 255) / 256;

@@ -344,10 +344,33 @@ down3_flat_kernel(const T *__restrict__ in, T *__restrict__ out, long planes, in
     }
 }
 
-// ---- up-like without a row loop: one thread per (plane, input row, 4 input columns) -> 2 x 8 outputs --------
+// ---- up-like without a row loop: one thread per (plane, input row, VI input columns) -> 2 x 2 VI outputs -----
 // Same idea as down3_flat_kernel: both input rows (i and i+1; the latter is re-read by the thread below, an L1 / L2
-// hit) are requested up front and the grid supplies the parallelism.
-template <typename TI, typename TO>
+// hit) are requested up front and the grid supplies the parallelism.  VI = 4 stores 8 outputs per row: one 16-byte
+// store for bf16, TWO for fp32 -- each of which then covers only every other 16 bytes across the warp (half sectors).
+// VI = 2 (fp32 outputs) makes the fp32 store one float4 per lane, contiguous across the warp.
+template <int VI> __device__ __forceinline__ void ld_cols(const float *p, float (&x)[VI + 1])
+{
+    if constexpr (VI == 4) {
+        const float4 v = ld4(p);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+        x[0] = v.x; x[1] = v.y;
+    }
+}
+template <int VI> __device__ __forceinline__ void ld_cols(const bf16 *p, float (&x)[VI + 1])
+{
+    if constexpr (VI == 4) {
+        const float4 v = ld4(p);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+        const uint32_t r = __ldg(reinterpret_cast<const uint32_t *>(p));
+        x[0] = __uint_as_float(r << 16); x[1] = __uint_as_float(r & 0xffff0000u);
+    }
+}
+
+template <typename TI, typename TO, int VI>
 __global__ void __launch_bounds__(256)
 up3_flat_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, int H, int W, int strips, int C,
                 long out_bstride, const __grid_constant__ Taps3 k)
@@ -357,19 +380,19 @@ up3_flat_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, in
     const unsigned pu = idx / per_plane, rem = idx - pu * per_plane;
     if (pu >= (unsigned long)planes) return;
     const unsigned i = rem / (unsigned)strips;
-    const int s = (int)(rem - i * (unsigned)strips), j = 4 * s;
+    const int s = (int)(rem - i * (unsigned)strips), j = VI * s;
     const TI *src = in + (long)pu * H * W + (long)i * W + j;
-    const bool has_r = (j + 4 < W), has_b = ((int)i + 1 < H);
-    const float4 ca = ld4(src);
-    float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ra = 0.f, rb = 0.f;
-    if (has_b) cb = ld4(src + W);
-    if (has_r) ra = ld1(src + 4);
-    if (has_r && has_b) rb = ld1(src + W + 4);
-    const float xa[5] = {ca.x, ca.y, ca.z, ca.w, ra}, xb[5] = {cb.x, cb.y, cb.z, cb.w, rb};
-    float e[8], o[8];
+    const bool has_r = (j + VI < W), has_b = ((int)i + 1 < H);
+    float xa[VI + 1], xb[VI + 1];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c <= VI; ++c) xa[c] = xb[c] = 0.f;
+    ld_cols<VI>(src, xa);
+    if (has_b) ld_cols<VI>(src + W, xb);
+    if (has_r) xa[VI] = ld1(src + VI);
+    if (has_r && has_b) xb[VI] = ld1(src + W + VI);
+    float e[2 * VI], o[2 * VI];
+#pragma unroll
+    for (int c = 0; c < VI; ++c) {
         e[2 * c] = k.k[1][1] * xa[c];
         e[2 * c + 1] = fmaf(k.k[1][2], xa[c + 1], k.k[1][0] * xa[c]);
         o[2 * c] = fmaf(k.k[2][1], xb[c], k.k[0][1] * xa[c]);
@@ -380,8 +403,13 @@ up3_flat_kernel(const TI *__restrict__ in, TO *__restrict__ out, long planes, in
     }
     const int W2 = 2 * W;
     TO *dst = out + strided_base(pu, C, out_bstride, 4L * H * W) + (long)(2 * i) * W2 + 2 * j;
-    st8(dst, e);
-    st8(dst + W2, o);
+    if constexpr (VI == 4) {
+        st8(dst, e);
+        st8(dst + W2, o);
+    } else {
+        st4(dst, make_float4(e[0], e[1], e[2], e[3]));
+        st4(dst + W2, make_float4(o[0], o[1], o[2], o[3]));
+    }
 }
 
 int group_planes(int plane_floats, long planes)
@@ -538,9 +566,16 @@ bool flat_down_wanted(int H, int W, int dtype)
     return m == 2 || (m == 1 && (dtype == AFR_F32 || (long)H * W <= 1024));
 }
 
-// AFR_UP_FLAT: 0 = never, 1 = fp32 planes up to 32 x 32 (default), 2 = always.  Measured (B200): fp32 16x16 planes
-// 0.79 -> 0.87, 32x32 0.86 -> 0.88, 64x64 0.92 -> 0.88 (the row-walking strips win once a plane is tall enough to
-// amortise their start-up); bf16: -0 .. -4 % everywhere.
+// AFR_UP_FLAT: 0 = never, 1 = every plane size when the OUTPUT is fp32 (default), 2 = always.  Measured (B200, fp32, of
+// the HBM peak, 4x4 ... 256x256 planes): 0.68 / 0.73 / 0.87 / 0.87 / 0.92 / 0.89 / 0.85 with the warp-shuffle, 4-column
+// flat and row-walking strip kernels -> 0.92 / 0.97 / 0.99 / 0.99 / 0.99 / 0.96 / 0.94 with two input columns per thread:
+// the 8 fp32 outputs per row of a 4-column thread are two 16-byte stores that each cover only every other 16 bytes
+// across the warp (half sectors); one float4 per lane is contiguous.  bf16 outputs (8 outputs = one 16-byte store
+// already): 2 columns 0.56, 4 columns -0 .. -4 % against the strip / warp kernels, so they stay there.
+#ifndef AFR_UP_FLAT_F32_COLS
+#define AFR_UP_FLAT_F32_COLS 2
+#endif
+
 static int up_flat_mode()
 {
     static const int v = []() { const char *e = getenv("AFR_UP_FLAT"); return e ? atoi(e) : 1; }();
@@ -549,23 +584,29 @@ static int up_flat_mode()
 
 bool flat_up_wanted(int H, int W, int in_dtype, int out_dtype)
 {
+    (void)H; (void)W; (void)in_dtype;
     const int m = up_flat_mode();
-    return m == 2 || (m == 1 && in_dtype == AFR_F32 && out_dtype == AFR_F32 && (long)H * W <= 1024);
+    return m == 2 || (m == 1 && out_dtype == AFR_F32);
 }
 
 cudaError_t flat_up_like(const void *in, void *out, long planes, int C, long out_bstride, int H, int W, const Taps3 &k,
                          int in_dtype, int out_dtype, cudaStream_t s)
 {
-    const int strips = W / 4;
+    // AFR_UP_FLAT_COLS = 2 | 4: input columns per thread (default: 2 for fp32 outputs, 4 for bf16 outputs)
+    static const int want_cols = []() { const char *e = getenv("AFR_UP_FLAT_COLS"); return e ? atoi(e) : 0; }();
+    const int vi = (want_cols == 2 || want_cols == 4) ? want_cols : (out_dtype == AFR_F32 ? AFR_UP_FLAT_F32_COLS : 4);
+    const int strips = W / vi;
     const long total = planes * (long)strips * H;
     const long grid = (total + 255) / 256;
     if (total >= 0xffffff00L || planes > 0x7fffffffL) return cudaErrorInvalidConfiguration;
-#define AFR_UF(TI, TO) up3_flat_kernel<TI, TO><<<(unsigned)grid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, H, W, strips, C, out_bstride, k)
+#define AFR_UF2(TI, TO, VI) up3_flat_kernel<TI, TO, VI><<<(unsigned)grid, 256, 0, s>>>((const TI *)in, (TO *)out, planes, H, W, strips, C, out_bstride, k)
+#define AFR_UF(TI, TO) do { if (vi == 2) AFR_UF2(TI, TO, 2); else AFR_UF2(TI, TO, 4); } while (0)
     if (in_dtype == AFR_F32 && out_dtype == AFR_F32) AFR_UF(float, float);
     else if (in_dtype == AFR_BF16 && out_dtype == AFR_BF16) AFR_UF(bf16, bf16);
     else if (in_dtype == AFR_BF16 && out_dtype == AFR_F32) AFR_UF(bf16, float);
     else AFR_UF(float, bf16);
 #undef AFR_UF
+#undef AFR_UF2
     return cudaGetLastError();
 }
 

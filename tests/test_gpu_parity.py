@@ -388,9 +388,9 @@ WARP_DOWN = {(4, 4), (8, 8), (16, 16), (8, 4), (4, 8), (16, 8), (8, 16), (2, 4),
 
 
 def _up_kernel_name(h, w, dtype=torch.float32):
-    if (h, w) in WARP_UP:
-        return "up3_warp_kernel"
-    return "up3_flat_kernel" if dtype == torch.float32 and h * w <= 1024 else "up3_kernel"
+    if dtype == torch.float32:           # fp32 outputs: the loop-free two-column kernel on every plane size
+        return "up3_flat_kernel"
+    return "up3_warp_kernel" if (h, w) in WARP_UP else "up3_kernel"
 
 
 def _down_kernel_name(h, w, dtype=torch.float32):

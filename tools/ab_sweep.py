@@ -39,7 +39,8 @@ def tm(fn, reps=7):
 
 FUSED = [(256, 128, 64, 64), (1024, 64, 32, 32), (64, 64, 128, 128), (16, 64, 256, 256), (4096, 64, 16, 16), (4096, 128, 8, 8),
          (4096, 256, 4, 4)]
-RES = [(4096, 256, 4, 4), (4096, 128, 8, 8), (4096, 64, 16, 16), (2048, 32, 32, 32), (256, 128, 64, 64)]
+RES = [(4096, 256, 4, 4), (4096, 128, 8, 8), (4096, 64, 16, 16), (2048, 32, 32, 32), (256, 128, 64, 64), (64, 64, 128, 128),
+       (16, 64, 256, 256)]
 rows = []
 for dt, es, dn in ((torch.float32, 4, "f32"), (torch.bfloat16, 2, "bf16")):
     if what in ("fused", "all", "fused_cl"):
